@@ -1,0 +1,432 @@
+"""codegraph-rust_b200 — ctypes binding over libcgvec_b200.so (include/cgvec.h) plus Python mirrors of
+the reference interfaces that sit on the similarity-search path, so the parity tests read like the
+reference's own tests:
+
+    ParallelVectorOps.parallel_top_k_search      crates/codegraph-vector/src/simd_ops.rs:361-383
+    B200VectorStore  (trait VectorStore)         crates/codegraph-core/src/traits.rs:11-16
+    B200Backend      (trait SurrealVectorBackend) crates/codegraph-vector/src/surreal_store.rs:11-22
+    SemanticSearch.search_by_embedding           crates/codegraph-vector/src/search.rs:91-144
+    GpuAcceleration.upload_vectors / compute_distances   crates/codegraph-vector/src/gpu.rs:221-291
+
+Every score and every top-k decision is computed by the CUDA library; this module only marshals
+buffers.  It never imports the oracle and has no CPU scoring path: without the built extension (or
+without an sm_100 GPU) it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import uuid as _uuid
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _build
+
+F32, F16 = 0, 1
+COSINE, DOT, L2 = 0, 1, 2
+FORMULA_SIMD, FORMULA_SCALAR, FORMULA_SEQ, FORMULA_BASELINE = 0, 1, 2, 3
+PATH_AUTO, PATH_EXACT, PATH_TENSOR = 0, 1, 2
+
+OK, ERR_BAD_ARG, ERR_BAD_DIM, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_NOT_FOUND, ERR_NO_DEVICE, ERR_UNSUPPORTED = (
+    0, -1, -2, -3, -4, -5, -6, -7, -8)
+
+EXPORTS = [
+    "cgvec_create", "cgvec_create_rank", "cgvec_nccl_unique_id", "cgvec_destroy", "cgvec_reserve", "cgvec_add",
+    "cgvec_add_f16", "cgvec_normalize_rows", "cgvec_fill_synthetic", "cgvec_len", "cgvec_dim", "cgvec_search",
+    "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
+    "cgvec_shard_range", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
+    "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_last_error", "cgvec_version",
+]
+
+
+class CgvecError(RuntimeError):
+    """Maps to CodeGraphError::Vector(msg) (codegraph-core/src/error.rs:18-19)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cgvec error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("metric", C.c_int), ("formula", C.c_int), ("path", C.c_int),
+                ("stream", C.c_void_p), ("device_io", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("searches", C.c_uint64), ("rows", C.c_uint64),
+                ("bytes_resident", C.c_uint64), ("sm_count", C.c_uint32), ("grid", C.c_uint32), ("block", C.c_uint32),
+                ("smem_bytes", C.c_uint32), ("stages", C.c_uint32), ("tile_rows", C.c_uint32),
+                ("last_scan_ms", C.c_float), ("scan_ms_total", C.c_double), ("scans_timed", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load_library(build: bool = True):
+    """Loads libcgvec_b200.so (building it first if sources are newer). Fails loudly if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build:
+        _build.build_lib()
+    if not os.path.exists(_build.LIB):
+        raise CgvecError(ERR_NO_DEVICE, f"{_build.LIB} is not built; run __graft_entry__.build()")
+    L = C.CDLL(_build.LIB)
+    vp, u64p, fp, u32p, u8p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p
+    L.cgvec_create.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.cgvec_create_rank.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, C.POINTER(vp)]
+    L.cgvec_nccl_unique_id.argtypes = [vp]
+    L.cgvec_destroy.argtypes = [vp]
+    L.cgvec_reserve.argtypes = [vp, C.c_uint64]
+    L.cgvec_add.argtypes = [vp, u8p, vp, C.c_uint64]
+    L.cgvec_add_f16.argtypes = [vp, u8p, vp, C.c_uint64]
+    L.cgvec_normalize_rows.argtypes = [vp]
+    L.cgvec_fill_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int]
+    L.cgvec_len.argtypes = [vp]; L.cgvec_len.restype = C.c_uint64
+    L.cgvec_dim.argtypes = [vp]; L.cgvec_dim.restype = C.c_uint32
+    L.cgvec_search.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, vp, vp]
+    L.cgvec_search_ex.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(SearchOpts), vp, vp, vp, vp]
+    L.cgvec_get.argtypes = [vp, vp, vp]
+    L.cgvec_get_row.argtypes = [vp, C.c_uint64, vp]
+    L.cgvec_get_rows.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.cgvec_row_of_id.argtypes = [vp, vp, u64p]
+    L.cgvec_rescore.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp]
+    L.cgvec_distances_first.argtypes = [vp, vp, C.c_uint64, vp, u64p]
+    L.cgvec_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+    L.cgvec_merge_topk_host.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, u32p]
+    L.cgvec_prefetch_k_basic.argtypes = [C.c_uint64]; L.cgvec_prefetch_k_basic.restype = C.c_uint64
+    L.cgvec_prefetch_k_filtered.argtypes = [C.c_uint64]; L.cgvec_prefetch_k_filtered.restype = C.c_uint64
+    L.cgvec_normalize_scores.argtypes = [vp, C.c_size_t]; L.cgvec_normalize_scores.restype = None
+    L.cgvec_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.cgvec_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.cgvec_last_error.restype = C.c_char_p
+    L.cgvec_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise CgvecError(rc, load_library().cgvec_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _ids_to_bytes(ids) -> Optional[np.ndarray]:
+    if ids is None:
+        return None
+    out = np.empty((len(ids), 16), np.uint8)
+    for i, x in enumerate(ids):
+        b = x.bytes if isinstance(x, _uuid.UUID) else bytes(x)
+        assert len(b) == 16
+        out[i] = np.frombuffer(b, np.uint8)
+    return out
+
+
+def version() -> str:
+    return load_library().cgvec_version().decode()
+
+
+# -------------------------------------------------------------------------------------------------
+# thin object wrapper over the C ABI
+# -------------------------------------------------------------------------------------------------
+class Index:
+    def __init__(self, dim: int, dtype: int = F32, device: int = 0, rank: int = 0, world: int = 1,
+                 nccl_unique_id: Optional[bytes] = None, row_offset: int = 0):
+        L = load_library()
+        self._h = C.c_void_p()
+        self.dim, self.dtype, self.device, self.rank, self.world, self.row_offset = dim, dtype, device, rank, world, row_offset
+        if world == 1 and rank == 0 and row_offset == 0:
+            dev = (C.c_int * 1)(device)
+            _check(L.cgvec_create(dim, dtype, dev, 1, C.byref(self._h)))
+        else:
+            buf = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id else None
+            _check(L.cgvec_create_rank(dim, dtype, device, rank, world, buf, row_offset, C.byref(self._h)))
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            load_library().cgvec_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(load_library().cgvec_len(self._h))
+
+    # -- write side
+    def reserve(self, n: int):
+        _check(load_library().cgvec_reserve(self._h, n))
+
+    def add(self, rows, ids=None):
+        L = load_library()
+        idb = _ids_to_bytes(ids)
+        if self.dtype == F32:
+            r = np.ascontiguousarray(rows, np.float32)
+            fn = L.cgvec_add
+        else:
+            r = np.asarray(rows)
+            r = np.ascontiguousarray(r if r.dtype == np.uint16 else r.astype(np.float16).view(np.uint16))
+            fn = L.cgvec_add_f16
+        if r.ndim != 2 or r.shape[1] != self.dim:
+            raise CgvecError(ERR_BAD_DIM, f"rows have shape {r.shape}, index dimension is {self.dim}")
+        if idb is not None and len(idb) != len(r):
+            raise CgvecError(ERR_BAD_ARG, "ids / rows length mismatch")
+        _check(fn(self._h, _ptr(idb), _ptr(r), r.shape[0]))
+
+    def normalize_rows(self):
+        _check(load_library().cgvec_normalize_rows(self._h))
+
+    def fill_synthetic(self, n: int, seed: int, unit_norm: bool = True):
+        _check(load_library().cgvec_fill_synthetic(self._h, n, seed, 1 if unit_norm else 0))
+
+    # -- read side
+    def search(self, queries, k: int, metric: int = COSINE, formula: int = FORMULA_SIMD, path: int = PATH_AUTO,
+               want_ids: bool = False):
+        """-> (rows u64[nq,k], scores f32[nq,k], counts u32[nq][, ids u8[nq,k,16]])"""
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise CgvecError(ERR_BAD_DIM, f"query dimension {q.shape[1]} != index dimension {self.dim}")
+        nq = q.shape[0]
+        rows = np.full((nq, max(k, 1)), 2**64 - 1, np.uint64)
+        scores = np.zeros((nq, max(k, 1)), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        ids = np.zeros((nq, max(k, 1), 16), np.uint8) if want_ids else None
+        o = SearchOpts(C.sizeof(SearchOpts), metric, formula, path, None, 0)
+        _check(load_library().cgvec_search_ex(self._h, _ptr(q), nq, k, C.byref(o), _ptr(rows), _ptr(ids), _ptr(scores), _ptr(counts)))
+        rows, scores = rows[:, :k], scores[:, :k]
+        if want_ids:
+            return rows, scores, counts, ids[:, :k]
+        return rows, scores, counts
+
+    def search_device(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int,
+                      metric: int = COSINE, stream: int = 0, path: int = PATH_AUTO):
+        """Device-resident I/O (raw device pointers); asynchronous on `stream`."""
+        o = SearchOpts(C.sizeof(SearchOpts), metric, FORMULA_SIMD, path, C.c_void_p(stream or None), 1)
+        _check(load_library().cgvec_search_ex(self._h, C.c_void_p(d_queries), nq, k, C.byref(o), C.c_void_p(d_rows), None,
+                                              C.c_void_p(d_scores), C.c_void_p(d_counts)))
+
+    def get_row(self, local_row: int) -> np.ndarray:
+        out = np.empty(self.dim, np.float32)
+        _check(load_library().cgvec_get_row(self._h, local_row, _ptr(out)))
+        return out
+
+    def get_rows(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), np.float32)
+        _check(load_library().cgvec_get_rows(self._h, first, n, _ptr(out)))
+        return out
+
+    def get(self, node_id) -> Optional[np.ndarray]:
+        b = _ids_to_bytes([node_id])
+        out = np.empty(self.dim, np.float32)
+        rc = load_library().cgvec_get(self._h, _ptr(b), _ptr(out))
+        if rc == ERR_NOT_FOUND:
+            return None
+        _check(rc)
+        return out
+
+    def row_of_id(self, node_id) -> Optional[int]:
+        b = _ids_to_bytes([node_id]); r = C.c_uint64()
+        rc = load_library().cgvec_row_of_id(self._h, _ptr(b), C.byref(r))
+        if rc == ERR_NOT_FOUND:
+            return None
+        _check(rc)
+        return int(r.value)
+
+    def rescore(self, query, local_rows, metric: int = COSINE, formula: int = FORMULA_SEQ) -> np.ndarray:
+        q = np.ascontiguousarray(query, np.float32)
+        if q.shape != (self.dim,):
+            raise CgvecError(ERR_BAD_DIM, f"query dimension {q.shape} != index dimension {self.dim}")
+        lr = np.ascontiguousarray(local_rows, np.uint64)
+        out = np.empty(len(lr), np.float32)
+        _check(load_library().cgvec_rescore(self._h, _ptr(q), _ptr(lr), len(lr), metric, formula, _ptr(out)))
+        return out
+
+    def distances_first(self, query, limit: int) -> np.ndarray:
+        q = np.ascontiguousarray(query, np.float32)
+        out = np.empty(max(min(limit, len(self)), 1), np.float32)
+        n = C.c_uint64()
+        _check(load_library().cgvec_distances_first(self._h, _ptr(q), limit, _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(load_library().cgvec_get_stats(self._h, C.byref(s)))
+        return s
+
+    def set_option(self, key: str, value: int):
+        _check(load_library().cgvec_set_option(self._h, key.encode(), value))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load_library().cgvec_nccl_unique_id(buf))
+    return buf.raw
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    b, e = C.c_uint64(), C.c_uint64()
+    _check(load_library().cgvec_shard_range(n, world, rank, C.byref(b), C.byref(e)))
+    return int(b.value), int(e.value)
+
+
+def merge_topk_host(rows, scores, counts, k: int, ascending: bool = False):
+    r = np.ascontiguousarray(rows, np.uint64); s = np.ascontiguousarray(scores, np.float32)
+    c = np.ascontiguousarray(counts, np.uint32)
+    parts = r.shape[0]
+    assert r.shape == (parts, k) and s.shape == (parts, k) and c.shape == (parts,)
+    orow = np.empty(max(k, 1), np.uint64); osc = np.empty(max(k, 1), np.float32); cnt = C.c_uint32()
+    _check(load_library().cgvec_merge_topk_host(_ptr(r), _ptr(s), _ptr(c), parts, k, 1 if ascending else 0, _ptr(orow), _ptr(osc), C.byref(cnt)))
+    return orow[: cnt.value].copy(), osc[: cnt.value].copy()
+
+
+def prefetch_k_basic(limit: int) -> int:
+    return int(load_library().cgvec_prefetch_k_basic(limit))
+
+
+def prefetch_k_filtered(limit: int) -> int:
+    return int(load_library().cgvec_prefetch_k_filtered(limit))
+
+
+def normalize_scores(scores) -> np.ndarray:
+    s = np.ascontiguousarray(scores, np.float32).copy()
+    load_library().cgvec_normalize_scores(_ptr(s), s.size)
+    return s
+
+
+# -------------------------------------------------------------------------------------------------
+# mirrors of the reference interfaces
+# -------------------------------------------------------------------------------------------------
+@dataclass
+class CodeNode:
+    """The two fields of codegraph_core::CodeNode (node.rs:4-16) the vector path reads."""
+    id: _uuid.UUID = field(default_factory=_uuid.uuid4)
+    embedding: Optional[Sequence[float]] = None
+
+
+class ParallelVectorOps:
+    """simd_ops.rs:343-383"""
+
+    @staticmethod
+    def parallel_top_k_search(query, embeddings, k: int, device: int = 0) -> List[Tuple[int, float]]:
+        emb = np.ascontiguousarray(embeddings, np.float32)
+        if emb.ndim != 2 or emb.shape[0] == 0:
+            return []
+        ix = Index(emb.shape[1], F32, device)
+        try:
+            ix.add(emb)
+            rows, scores, counts = ix.search(query, k, COSINE)
+            return [(int(rows[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+        finally:
+            ix.close()
+
+
+class B200VectorStore:
+    """trait VectorStore (codegraph-core/src/traits.rs:11-16) over one GPU-resident index."""
+
+    def __init__(self, dimension: int, dtype: int = F32, device: int = 0):
+        self.index = Index(dimension, dtype, device)
+
+    def store_embeddings(self, nodes: Sequence[CodeNode]) -> None:
+        withemb = [n for n in nodes if n.embedding is not None]       # nodes without an embedding are skipped
+        if not withemb:                                                # (graph_vector.rs:472-476)
+            return
+        rows = np.asarray([n.embedding for n in withemb], np.float32)
+        self.index.add(rows, [n.id for n in withemb])
+
+    def search_similar(self, query_embedding, limit: int) -> List[_uuid.UUID]:
+        q = np.asarray(query_embedding, np.float32)
+        if q.size == 0 or limit == 0:                                  # surreal_store.rs:62-64
+            return []
+        _, _, counts, ids = self.index.search(q, limit, COSINE, want_ids=True)
+        return [_uuid.UUID(bytes=ids[0, i].tobytes()) for i in range(int(counts[0]))]
+
+    def get_embedding(self, node_id: _uuid.UUID) -> Optional[List[float]]:
+        r = self.index.get(node_id)
+        return None if r is None else r.tolist()
+
+
+class B200Backend:
+    """trait SurrealVectorBackend (surreal_store.rs:11-22): ("nodes:<uuid>", cosine DISTANCE) ascending."""
+
+    def __init__(self, store: B200VectorStore):
+        self.store = store
+        self.last_column = None
+
+    def upsert_nodes(self, nodes: Sequence[CodeNode]) -> None:
+        self.store.store_embeddings(nodes)
+
+    def vector_knn(self, column: str, query_embedding, limit: int, ef_search: int = 0) -> List[Tuple[str, float]]:
+        self.last_column = column
+        q = np.asarray(query_embedding, np.float32)
+        if q.size == 0 or limit == 0:
+            return []
+        _, scores, counts, ids = self.store.index.search(q, limit, COSINE, want_ids=True)
+        return [(f"nodes:{_uuid.UUID(bytes=ids[0, i].tobytes())}", float(np.float32(1.0) - scores[0, i]))
+                for i in range(int(counts[0]))]
+
+    def get_node_embedding(self, node_id: _uuid.UUID):
+        return self.store.get_embedding(node_id)
+
+
+@dataclass
+class SearchResult:
+    node_id: _uuid.UUID
+    score: float
+
+
+class SemanticSearch:
+    """search.rs:14-144: over-fetch through the trait, exact re-score (search.rs:519-533 arithmetic, on the
+    device via cgvec_rescore), stable sort descending, truncate, min-max normalise."""
+
+    def __init__(self, vector_store: B200VectorStore):
+        self.vector_store = vector_store
+
+    def search_by_embedding(self, query_embedding, limit: int) -> List[SearchResult]:
+        prefetch_k = prefetch_k_basic(limit)                                       # search.rs:113
+        ids = self.vector_store.search_similar(query_embedding, prefetch_k)        # search.rs:114-117
+        if not ids:
+            return []
+        ix = self.vector_store.index
+        local = [ix.row_of_id(i) for i in ids]
+        raw = ix.rescore(query_embedding, local, COSINE, FORMULA_SEQ)              # search.rs:120-129, :207-217
+        order = sorted(range(len(ids)), key=lambda j: (-(raw[j]) if raw[j] == raw[j] else np.inf, j))   # :132-136 (stable)
+        order = order[:limit]
+        norm = normalize_scores(raw[order])                                        # search.rs:138
+        return [SearchResult(ids[j], float(s)) for j, s in zip(order, norm)]
+
+
+class GpuAcceleration:
+    """gpu.rs:109-381 API shape: upload_vectors(flat, dimension) -> data handle; compute_distances(query, data, limit)."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def upload_vectors(self, vectors, dimension: int) -> Index:
+        flat = np.ascontiguousarray(vectors, np.float32).reshape(-1)
+        if flat.size % dimension != 0:                                             # gpu.rs:226-230
+            raise CgvecError(ERR_BAD_ARG, "Vector data length not divisible by dimension")
+        ix = Index(dimension, F32, self.device)
+        ix.add(flat.reshape(-1, dimension))
+        return ix
+
+    def compute_distances(self, query, gpu_data: Index, limit: int) -> np.ndarray:
+        q = np.asarray(query, np.float32)
+        if q.size != gpu_data.dim:                                                 # gpu.rs:265-271
+            raise CgvecError(ERR_BAD_DIM, f"Query dimension {q.size} doesn't match GPU data dimension {gpu_data.dim}")
+        return gpu_data.distances_first(q, limit)

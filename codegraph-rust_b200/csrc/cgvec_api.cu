@@ -1,0 +1,1027 @@
+// cgvec_api.cu — the C ABI of libcgvec_b200.so (include/cgvec.h): index lifecycle, the write side
+// (store_embeddings), the search orchestration (scan -> per-CTA partials -> merge -> [NCCL all-gather ->
+// merge] -> decode) and the host-side helpers.  No CPU scoring path exists in this file: without an
+// sm_100 device every compute entry point returns CGVEC_ERR_NO_DEVICE.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cgvec.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "nccl_dyn.h"
+#include "scan_exact.cuh"
+
+#define CGVEC_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+using namespace cgv;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? CGVEC_ERR_OOM                                \
+                        : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? CGVEC_ERR_NO_DEVICE \
+                                                                                          : CGVEC_ERR_CUDA; \
+            return fail(code_, "%s failed: %s", #expr, cudaGetErrorString(e_));                          \
+        }                                                                                                \
+    } while (0)
+
+#define NCCL_TRY(expr)                                                                           \
+    do {                                                                                         \
+        int r_ = (expr);                                                                         \
+        if (r_ != kNcclSuccess) return fail(CGVEC_ERR_NCCL, "%s failed: %s", #expr, nccl_api().GetErrorString(r_)); \
+    } while (0)
+
+constexpr uint32_t kMaxK = 1024;
+constexpr uint32_t kSmemBudget = 227 * 1024;
+constexpr uint32_t kMergeMaxKeys = 8192;
+
+struct IdKey {
+    uint64_t lo, hi;
+    bool operator==(const IdKey& o) const { return lo == o.lo && hi == o.hi; }
+};
+struct IdHash {
+    size_t operator()(const IdKey& k) const {
+        uint64_t x = k.lo * 0x9E3779B97F4A7C15ull ^ (k.hi + 0x7F4A7C15ull + (k.lo << 6) + (k.lo >> 2));
+        return (size_t)(x ^ (x >> 29));
+    }
+};
+IdKey id_key(const uint8_t id[16]) {
+    IdKey k;
+    memcpy(&k.lo, id, 8);
+    memcpy(&k.hi, id + 8, 8);
+    return k;
+}
+
+uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Per-call scratch: a stream, device buffers and pinned host mirrors.  Pooled so that search() is
+// reentrant from many host threads (multi_vector_search fans out concurrent calls, search.rs:358-361).
+struct SearchCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    float* d_q = nullptr;        size_t q_cap = 0;       // floats
+    uint64_t* d_part[2] = {nullptr, nullptr}; size_t part_cap = 0;   // keys
+    uint64_t* d_gather = nullptr; size_t gather_cap = 0;  // keys
+    uint64_t* d_rows = nullptr;  float* d_scores = nullptr; uint32_t* d_counts = nullptr; size_t out_cap = 0, cnt_cap = 0;
+    uint64_t* d_tmp_rows = nullptr; float* d_tmp_scores = nullptr; size_t tmp_cap = 0;
+    float* h_q = nullptr;        size_t hq_cap = 0;
+    uint64_t* h_rows = nullptr;  float* h_scores = nullptr; uint32_t* h_counts = nullptr; size_t hout_cap = 0, hcnt_cap = 0;
+};
+
+struct ScanGeom {
+    uint32_t tile_rows, stages, sync_interval, cand_cap, row_words, grid, smem;
+};
+
+struct Index {
+    uint32_t dim = 0, ld = 0, esize = 4;
+    cgvec_dtype dtype = CGVEC_F32;
+    int device = 0;
+    int rank = 0, world = 1;
+    uint64_t row_offset = 0;
+    int sm_count = 0;
+
+    void* d_rows = nullptr;
+    float* d_norms = nullptr;
+    uint64_t n = 0, cap = 0;
+
+    std::vector<uint8_t> ids;     // 16 bytes per local row
+    std::vector<uint8_t> has_id;  // 1 per local row
+    std::unordered_map<IdKey, uint64_t, IdHash> id2row;
+
+    nccl_comm_t comm = nullptr;
+    std::mutex comm_mu;           // collectives must be issued in the same order on every rank
+
+    std::mutex pool_mu;
+    std::vector<SearchCtx*> pool;
+    cudaStream_t main_stream = nullptr;
+
+    // knobs (cgvec_set_option)
+    int opt_tile_rows = 0, opt_stages = 0, opt_sync = 0, opt_l2_hint = 0, opt_grid = 0, opt_timing = 0, opt_max_nq = kScanMaxQ;
+
+    // stats
+    std::atomic<uint64_t> launches{0}, searches{0};
+    ScanGeom last_geom{};
+    std::mutex ev_mu;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // scan kernel brackets awaiting readout
+    double scan_ms_total = 0.0;
+    uint64_t scan_timed = 0;
+    float last_scan_ms = 0.0f;
+};
+
+int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(CGVEC_ERR_NO_DEVICE, "no CUDA device available (%s); libcgvec_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(CGVEC_ERR_BAD_ARG, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CGVEC_ERR_NO_DEVICE, "device %d is sm_%d%d; libcgvec_b200 is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    return CGVEC_OK;
+}
+
+template <typename T>
+int ensure(T** p, size_t* cap, size_t need, bool pinned = false) {
+    if (need <= *cap && *p) return CGVEC_OK;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; }
+    size_t c = need < 64 ? 64 : need;
+    if (pinned) CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(p), c * sizeof(T)));
+    else CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), c * sizeof(T)));
+    *cap = c;
+    return CGVEC_OK;
+}
+
+int ctx_acquire(Index* ix, SearchCtx** out) {
+    {
+        std::lock_guard<std::mutex> g(ix->pool_mu);
+        if (!ix->pool.empty()) { *out = ix->pool.back(); ix->pool.pop_back(); return CGVEC_OK; }
+    }
+    auto* c = new SearchCtx();
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete c; return fail(CGVEC_ERR_CUDA, "stream/event create failed: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return CGVEC_OK;
+}
+void ctx_release(Index* ix, SearchCtx* c) {
+    std::lock_guard<std::mutex> g(ix->pool_mu);
+    ix->pool.push_back(c);
+}
+void ctx_free(SearchCtx* c) {
+    cudaFree(c->d_q); cudaFree(c->d_part[0]); cudaFree(c->d_part[1]); cudaFree(c->d_gather);
+    cudaFree(c->d_rows); cudaFree(c->d_scores); cudaFree(c->d_counts); cudaFree(c->d_tmp_rows); cudaFree(c->d_tmp_scores);
+    cudaFreeHost(c->h_q); cudaFreeHost(c->h_rows); cudaFreeHost(c->h_scores); cudaFreeHost(c->h_counts);
+    if (c->done) cudaEventDestroy(c->done);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int grow(Index* ix, uint64_t need, bool exact = false) {
+    if (need <= ix->cap) return CGVEC_OK;
+    uint64_t newcap = ix->cap ? ix->cap * 2 : 1024;
+    if (newcap < need || exact) newcap = need;
+    void* nrows = nullptr;
+    float* nnorms = nullptr;
+    size_t row_bytes = (size_t)ix->ld * ix->esize;
+    cudaError_t e = cudaMalloc(&nrows, newcap * row_bytes + 256);
+    if (e != cudaSuccess && newcap > need) {   // doubling did not fit: fall back to the exact size
+        cudaGetLastError();
+        newcap = need;
+        e = cudaMalloc(&nrows, newcap * row_bytes + 256);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(CGVEC_ERR_OOM, "cudaMalloc of %zu bytes for %llu rows failed: %s", newcap * row_bytes, (unsigned long long)newcap, cudaGetErrorString(e)); }
+    e = cudaMalloc(reinterpret_cast<void**>(&nnorms), (newcap + 64) * sizeof(float));
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(nrows); return fail(CGVEC_ERR_OOM, "cudaMalloc for norms failed: %s", cudaGetErrorString(e)); }
+    CUDA_TRY(cudaMemsetAsync(nnorms, 0, (newcap + 64) * sizeof(float), ix->main_stream));
+    if (ix->n) {
+        CUDA_TRY(cudaMemcpyAsync(nrows, ix->d_rows, ix->n * row_bytes, cudaMemcpyDeviceToDevice, ix->main_stream));
+        CUDA_TRY(cudaMemcpyAsync(nnorms, ix->d_norms, ix->n * sizeof(float), cudaMemcpyDeviceToDevice, ix->main_stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    cudaFree(ix->d_rows);
+    cudaFree(ix->d_norms);
+    ix->d_rows = nrows;
+    ix->d_norms = nnorms;
+    ix->cap = newcap;
+    return CGVEC_OK;
+}
+
+ScanParams map_params(const Index* ix) {
+    ScanParams p{};
+    p.row_offset = ix->row_offset;
+    p.blk_rows = 1u << 30;
+    p.n_shards = 1;
+    p.shard_id = 0;
+    return p;
+}
+
+int launch_norms(Index* ix, uint64_t first, uint64_t count, cudaStream_t st) {
+    if (!count) return CGVEC_OK;
+    const int threads = 256;
+    uint64_t blocks = (count * 8 + threads - 1) / threads;
+    if (ix->dtype == CGVEC_F32)
+        row_sqnorm_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(static_cast<const float*>(ix->d_rows), first, count, ix->dim, ix->ld, ix->d_norms);
+    else
+        row_sqnorm_kernel<__half><<<(unsigned)blocks, threads, 0, st>>>(static_cast<const __half*>(ix->d_rows), first, count, ix->dim, ix->ld, ix->d_norms);
+    ix->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CGVEC_OK;
+}
+
+// ---- scan planning / launch ---------------------------------------------------------------------
+int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
+    g->row_words = scan_row_words(ix->ld, ix->esize);
+    const uint32_t try_tiles[4] = {16, 8, 4, 32};
+    for (int t = 0; t < 4; ++t) {
+        uint32_t tile = ix->opt_tile_rows ? (uint32_t)ix->opt_tile_rows : try_tiles[t];
+        if (tile != 4 && tile != 8 && tile != 16 && tile != 32) return fail(CGVEC_ERR_BAD_ARG, "tile_rows must be 4, 8, 16 or 32");
+        uint32_t ngroups = kScanConsumerWarps / (tile / 4);
+        uint32_t sync = ix->opt_sync ? (uint32_t)ix->opt_sync : 8;
+        sync = ((sync + ngroups - 1) / ngroups) * ngroups;
+        uint32_t cand = next_pow2(k + sync * tile);
+        if (cand < 64) cand = 64;
+        uint32_t max_stages = ix->opt_stages ? (uint32_t)ix->opt_stages : 8;
+        for (uint32_t s = max_stages; s >= 2; --s) {
+            ScanSmemLayout L = scan_smem_layout(g->row_words, tile, s, ix->dim, nq, cand);
+            if (L.total <= kSmemBudget) {
+                g->tile_rows = tile; g->stages = s; g->sync_interval = sync; g->cand_cap = cand; g->smem = L.total;
+                uint64_t tiles = (ix->n + tile - 1) / tile;
+                uint32_t grid = ix->opt_grid ? (uint32_t)ix->opt_grid : (uint32_t)ix->sm_count;
+                g->grid = (uint32_t)(tiles < grid ? tiles : grid);
+                if (g->grid == 0) g->grid = 1;
+                return CGVEC_OK;
+            }
+        }
+        if (ix->opt_tile_rows) break;
+    }
+    return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u (k=%u, nq=%u) does not fit the scan kernel's shared memory", ix->dim, k, nq);
+}
+
+template <typename T, int METRIC, int NQ>
+int launch_scan_t(const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(scan_exact_kernel<T, METRIC, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    });
+    if (attr_err != cudaSuccess) return fail(CGVEC_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(attr_err));
+    scan_exact_kernel<T, METRIC, NQ><<<g.grid, kScanThreads, g.smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return CGVEC_OK;
+}
+template <typename T, int METRIC>
+int launch_scan_q(uint32_t nq, const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
+    switch (nq) {
+        case 1: return launch_scan_t<T, METRIC, 1>(p, g, st);
+        case 2: return launch_scan_t<T, METRIC, 2>(p, g, st);
+        case 4: return launch_scan_t<T, METRIC, 4>(p, g, st);
+    }
+    return fail(CGVEC_ERR_BAD_ARG, "internal: scan batch %u", nq);
+}
+template <typename T>
+int launch_scan_m(int metric, uint32_t nq, const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
+    switch (metric) {
+        case CGVEC_COSINE: return launch_scan_q<T, METRIC_COSINE>(nq, p, g, st);
+        case CGVEC_DOT: return launch_scan_q<T, METRIC_DOT>(nq, p, g, st);
+        case CGVEC_L2: return launch_scan_q<T, METRIC_L2>(nq, p, g, st);
+    }
+    return fail(CGVEC_ERR_BAD_ARG, "unknown metric %d", metric);
+}
+
+// Merge `lists` key lists per query (element (q, l, i) at in[q*q_stride + l*l_stride + i]) down to one list of k.
+// The final level decodes into d_rows/d_scores/d_counts when given, and/or writes keys to `final_keys`.
+int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32_t lists, uint32_t k, int ascending,
+                uint64_t* final_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, cudaStream_t st,
+                size_t q_stride, size_t l_stride) {
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMaxKeys * 8); });
+    // the kernel reads list l of query q at in + (q*n_lists + l)*k: repack when the caller's layout differs
+    const uint64_t* cur = in;
+    uint32_t cur_lists = lists;
+    int pp = 0;
+    if (!(q_stride == (size_t)lists * k && l_stride == k)) {
+        // gathered layout [list][nq][k] -> [nq][list][k] with strided 2D copies (device to device)
+        uint64_t* dst = c->d_part[0];
+        for (uint32_t q = 0; q < nq; ++q)
+            CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)q * lists * k, (size_t)k * 8, in + q * q_stride, l_stride * 8, (size_t)k * 8, lists,
+                                       cudaMemcpyDeviceToDevice, st));
+        cur = dst;
+        pp = 1;
+    }
+    const uint32_t per_cta_max = kMergeMaxKeys / k < 2 ? 2 : kMergeMaxKeys / k;
+    while (true) {
+        uint32_t per_cta = cur_lists < per_cta_max ? cur_lists : per_cta_max;
+        uint32_t n_out = (cur_lists + per_cta - 1) / per_cta;
+        uint32_t sort_n = next_pow2(per_cta * k);
+        if (sort_n < 2) sort_n = 2;
+        const bool last = (n_out == 1);
+        uint64_t* out = last ? final_keys : c->d_part[pp];
+        dim3 grid(n_out, nq);
+        merge_topk_kernel<<<grid, kMergeThreads, sort_n * 8, st>>>(cur, cur_lists, k, per_cta, sort_n, out, ascending,
+                                                                  last ? d_rows : nullptr, last ? d_scores : nullptr,
+                                                                  last ? d_counts : nullptr);
+        ix->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (last) break;
+        cur = out;
+        cur_lists = n_out;
+        pp ^= 1;
+    }
+    return CGVEC_OK;
+}
+
+// One exact-order scan of the local shard for `nq` (1, 2 or 4) queries already on the device at `d_q`
+// (stride = dim rounded up to 4 floats), leaving either decoded results or (world > 1) merged global keys.
+int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
+               uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    ScanGeom g;
+    int rc = plan_scan(ix, k, nq, &g);
+    if (rc) return rc;
+    const int ascending = (metric == CGVEC_L2);
+    size_t need_part = (size_t)nq * (g.grid > (uint32_t)ix->world ? g.grid : ix->world) * k;
+    if (need_part > c->part_cap) {
+        size_t cap0 = c->part_cap, cap1 = c->part_cap;
+        rc = ensure(&c->d_part[0], &cap0, need_part); if (rc) return rc;
+        rc = ensure(&c->d_part[1], &cap1, need_part); if (rc) return rc;
+        c->part_cap = cap0 < cap1 ? cap0 : cap1;
+    }
+    ScanParams p = map_params(ix);
+    p.rows = ix->d_rows; p.norms = ix->d_norms; p.queries = d_q; p.partials = c->d_part[0];
+    p.n_rows = ix->n; p.d = ix->dim; p.ld = ix->ld; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
+    p.stages = g.stages; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ix->opt_timing) {
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, st));
+    }
+    rc = (ix->dtype == CGVEC_F32) ? launch_scan_m<float>(metric, nq, p, g, st) : launch_scan_m<__half>(metric, nq, p, g, st);
+    if (rc) return rc;
+    ix->launches++;
+    if (ix->opt_timing) {
+        CUDA_TRY(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(ix->ev_mu);
+        ix->timed.emplace_back(e0, e1);
+    }
+    ix->last_geom = g;
+
+    if (ix->world == 1) {
+        return merge_lists(ix, c, c->d_part[0], nq, g.grid, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)g.grid * k, k);
+    }
+    // sharded: local best-k keys -> one NCCL all-gather -> every rank merges the `world` lists
+    size_t per_rank = (size_t)nq * k;
+    size_t cap_g = c->gather_cap;
+    rc = ensure(&c->d_gather, &cap_g, per_rank * (ix->world + 1)); if (rc) return rc;
+    c->gather_cap = cap_g;
+    uint64_t* local_keys = c->d_gather + per_rank * ix->world;
+    rc = merge_lists(ix, c, c->d_part[0], nq, g.grid, k, ascending, local_keys, nullptr, nullptr, nullptr, st, (size_t)g.grid * k, k);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(ix->comm_mu);
+        NCCL_TRY(nccl_api().AllGather(local_keys, c->d_gather, per_rank, kNcclUint64, ix->comm, st));
+    }
+    return merge_lists(ix, c, c->d_gather, nq, ix->world, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)k, per_rank);
+}
+
+void drain_timings(Index* ix) {
+    std::lock_guard<std::mutex> lk(ix->ev_mu);
+    for (auto& pr : ix->timed) {
+        if (cudaEventSynchronize(pr.second) == cudaSuccess) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+                ix->scan_ms_total += ms; ix->scan_timed++; ix->last_scan_ms = ms;
+            }
+        }
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    ix->timed.clear();
+}
+
+}  // namespace
+
+struct cgvec_index : Index {};
+
+// ================================================================================================
+// lifecycle
+// ================================================================================================
+static int create_common(uint32_t dim, cgvec_dtype storage, int device, int rank, int world, const void* uid,
+                         uint64_t row_offset, cgvec_index** out) {
+    if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (dim == 0) return fail(CGVEC_ERR_BAD_DIM, "dimension must be > 0");
+    if (storage != CGVEC_F32 && storage != CGVEC_F16) return fail(CGVEC_ERR_BAD_ARG, "unknown storage dtype %d", (int)storage);
+    if (world < 1 || rank < 0 || rank >= world) return fail(CGVEC_ERR_BAD_ARG, "bad rank %d / world %d", rank, world);
+    int rc = check_device(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<cgvec_index> ix(new cgvec_index());
+    ix->dim = dim;
+    ix->dtype = storage;
+    ix->esize = storage == CGVEC_F32 ? 4 : 2;
+    const uint32_t align_elems = 16 / ix->esize;                 // rows start on 16-byte boundaries (bulk copies)
+    ix->ld = (dim + align_elems - 1) / align_elems * align_elems;
+    ix->device = device;
+    ix->rank = rank;
+    ix->world = world;
+    ix->row_offset = row_offset;
+    CUDA_TRY(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ix->main_stream, cudaStreamNonBlocking));
+    if (world > 1) {
+        if (!uid) return fail(CGVEC_ERR_BAD_ARG, "world > 1 needs the NCCL unique id from cgvec_nccl_unique_id()");
+        if (!nccl_api().load()) return fail(CGVEC_ERR_NCCL, "%s", nccl_api().load_error);
+        NcclUniqueId id;
+        memcpy(&id, uid, sizeof(id));
+        NCCL_TRY(nccl_api().CommInitRank(&ix->comm, world, id, rank));
+    }
+    *out = ix.release();
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_create(uint32_t dim, cgvec_dtype storage, const int* device_ids, int n_devices, cgvec_index** out) {
+    if (n_devices < 1) return fail(CGVEC_ERR_BAD_ARG, "n_devices must be >= 1");
+    if (n_devices > 1)
+        return fail(CGVEC_ERR_UNSUPPORTED, "single-process multi-device indexes are not built yet: use one cgvec_create_rank per GPU");
+    return create_common(dim, storage, device_ids ? device_ids[0] : 0, 0, 1, nullptr, 0, out);
+}
+
+CGVEC_EXPORT int cgvec_create_rank(uint32_t dim, cgvec_dtype storage, int device, int rank, int world, const void* nccl_unique_id,
+                                   uint64_t row_offset, cgvec_index** out) {
+    return create_common(dim, storage, device, rank, world, nccl_unique_id, row_offset, out);
+}
+
+CGVEC_EXPORT int cgvec_nccl_unique_id(void* out_128_bytes) {
+    if (!out_128_bytes) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    if (!nccl_api().load()) return fail(CGVEC_ERR_NCCL, "%s", nccl_api().load_error);
+    NcclUniqueId id;
+    NCCL_TRY(nccl_api().GetUniqueId(&id));
+    memcpy(out_128_bytes, &id, sizeof(id));
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
+    if (!ix) return CGVEC_OK;
+    cudaSetDevice(ix->device);
+    cudaDeviceSynchronize();
+    drain_timings(ix);
+    for (auto* c : ix->pool) ctx_free(c);
+    if (ix->comm) nccl_api().CommDestroy(ix->comm);
+    cudaFree(ix->d_rows);
+    cudaFree(ix->d_norms);
+    if (ix->main_stream) cudaStreamDestroy(ix->main_stream);
+    delete ix;
+    return CGVEC_OK;
+}
+
+// ================================================================================================
+// write side
+// ================================================================================================
+CGVEC_EXPORT int cgvec_reserve(cgvec_index* ix, uint64_t n_rows) {
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    return grow(ix, n_rows, /*exact=*/true);
+}
+
+static int add_impl(cgvec_index* ix, const uint8_t (*ids)[16], const void* rows, uint64_t n, uint32_t src_esize) {
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (n == 0) return CGVEC_OK;
+    if (!rows) return fail(CGVEC_ERR_BAD_ARG, "rows is NULL");
+    if (src_esize != ix->esize)
+        return fail(CGVEC_ERR_BAD_ARG, "index stores %s rows; use %s", ix->esize == 4 ? "f32" : "f16", ix->esize == 4 ? "cgvec_add" : "cgvec_add_f16");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    // classify: append vs overwrite (InMemoryVectorStore insert semantics)
+    std::vector<uint64_t> target(n);
+    uint64_t next = ix->n;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (ids) {
+            IdKey key = id_key(ids[i]);
+            auto it = ix->id2row.find(key);
+            if (it != ix->id2row.end()) { target[i] = it->second; continue; }
+            ix->id2row.emplace(key, next);
+        }
+        target[i] = next++;
+    }
+    if (ix->row_offset + next > 0xfffffffeull) return fail(CGVEC_ERR_UNSUPPORTED, "more than 2^32-2 rows are not supported");
+    int rc = grow(ix, next);
+    if (rc) return rc;
+    ix->ids.resize(next * 16, 0);
+    ix->has_id.resize(next, 0);
+    const size_t src_pitch = (size_t)ix->dim * ix->esize, dst_pitch = (size_t)ix->ld * ix->esize;
+    const uint8_t* src = static_cast<const uint8_t*>(rows);
+    uint8_t* dst = static_cast<uint8_t*>(ix->d_rows);
+    uint64_t i = 0;
+    while (i < n) {                     // copy maximal runs with consecutive targets in one 2D copy
+        uint64_t j = i + 1;
+        while (j < n && target[j] == target[j - 1] + 1) ++j;
+        if (dst_pitch != src_pitch) CUDA_TRY(cudaMemset2DAsync(dst + target[i] * dst_pitch, dst_pitch, 0, dst_pitch, j - i, ix->main_stream));
+        CUDA_TRY(cudaMemcpy2DAsync(dst + target[i] * dst_pitch, dst_pitch, src + i * src_pitch, src_pitch, src_pitch, j - i,
+                                   cudaMemcpyHostToDevice, ix->main_stream));
+        rc = launch_norms(ix, target[i], j - i, ix->main_stream);
+        if (rc) return rc;
+        if (ids) for (uint64_t r = i; r < j; ++r) { memcpy(&ix->ids[target[r] * 16], ids[r], 16); ix->has_id[target[r]] = 1; }
+        i = j;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    ix->n = next;
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_add(cgvec_index* ix, const uint8_t (*ids)[16], const float* rows_f32, uint64_t n) {
+    return add_impl(ix, ids, rows_f32, n, 4);
+}
+CGVEC_EXPORT int cgvec_add_f16(cgvec_index* ix, const uint8_t (*ids)[16], const uint16_t* rows_f16, uint64_t n) {
+    return add_impl(ix, ids, rows_f16, n, 2);
+}
+
+CGVEC_EXPORT int cgvec_normalize_rows(cgvec_index* ix) {
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (!ix->n) return CGVEC_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const int threads = 256;
+    uint64_t blocks = (ix->n * 8 + threads - 1) / threads;
+    if (ix->dtype == CGVEC_F32) normalize_rows_kernel<float><<<(unsigned)blocks, threads, 0, ix->main_stream>>>(static_cast<float*>(ix->d_rows), ix->n, ix->dim, ix->ld);
+    else normalize_rows_kernel<__half><<<(unsigned)blocks, threads, 0, ix->main_stream>>>(static_cast<__half*>(ix->d_rows), ix->n, ix->dim, ix->ld);
+    ix->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int rc = launch_norms(ix, 0, ix->n, ix->main_stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_fill_synthetic(cgvec_index* ix, uint64_t n, uint64_t seed, int unit_norm) {
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (!n) return CGVEC_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    uint64_t next = ix->n + n;
+    if (ix->row_offset + next > 0xfffffffeull) return fail(CGVEC_ERR_UNSUPPORTED, "more than 2^32-2 rows are not supported");
+    int rc = grow(ix, next);
+    if (rc) return rc;
+    ix->ids.resize(next * 16, 0);
+    ix->has_id.resize(next, 0);
+    const int threads = 256;
+    ScanParams map = map_params(ix);
+    const uint64_t chunk = 1ull << 22;          // keep each grid < 2^31 blocks
+    for (uint64_t done = 0; done < n; done += chunk) {
+        uint64_t cnt = n - done < chunk ? n - done : chunk;
+        uint64_t blocks = (cnt * 8 + threads - 1) / threads;
+        if (ix->dtype == CGVEC_F32)
+            synth_rows_kernel<float><<<(unsigned)blocks, threads, 0, ix->main_stream>>>(static_cast<float*>(ix->d_rows), ix->n + done, cnt, ix->dim, ix->ld, seed, unit_norm, map);
+        else
+            synth_rows_kernel<__half><<<(unsigned)blocks, threads, 0, ix->main_stream>>>(static_cast<__half*>(ix->d_rows), ix->n + done, cnt, ix->dim, ix->ld, seed, unit_norm, map);
+        ix->launches++;
+        CUDA_TRY(cudaGetLastError());
+        rc = launch_norms(ix, ix->n + done, cnt, ix->main_stream);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    ix->n = next;
+    return CGVEC_OK;
+}
+
+// ================================================================================================
+// read side
+// ================================================================================================
+CGVEC_EXPORT uint64_t cgvec_len(const cgvec_index* ix) { return ix ? ix->n : 0; }
+CGVEC_EXPORT uint32_t cgvec_dim(const cgvec_index* ix) { return ix ? ix->dim : 0; }
+
+// formula != SIMD: over-fetch with the exact SIMD-order scan, re-score the candidates in the requested
+// formula on the device, re-rank, and PROVE no outside row can enter the top-k (else widen and retry).
+static int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st,
+                          uint64_t* h_rows, float* h_scores, uint32_t* h_count);
+
+CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, uint32_t nq, uint32_t k,
+                                 const cgvec_search_opts* opts, uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores,
+                                 uint32_t* out_counts) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    cgvec_search_opts o{};
+    o.struct_size = sizeof(o);
+    if (opts) {
+        if (opts->struct_size < sizeof(uint32_t) * 4) return fail(CGVEC_ERR_BAD_ARG, "opts->struct_size is not set");
+        memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
+    }
+    if (o.metric != CGVEC_COSINE && o.metric != CGVEC_DOT && o.metric != CGVEC_L2) return fail(CGVEC_ERR_BAD_ARG, "unknown metric %d", (int)o.metric);
+    if (o.formula < CGVEC_FORMULA_SIMD || o.formula > CGVEC_FORMULA_BASELINE) return fail(CGVEC_ERR_BAD_ARG, "unknown formula %d", (int)o.formula);
+    if (o.formula != CGVEC_FORMULA_SIMD && o.metric != CGVEC_COSINE)
+        return fail(CGVEC_ERR_UNSUPPORTED, "formulas other than SIMD exist for cosine only (the reference has no scalar dot / L2)");
+    if (o.path == CGVEC_PATH_TENSOR) return fail(CGVEC_ERR_UNSUPPORTED, "tensor-core batched path is not built yet");
+    if (o.device_io && out_ids) return fail(CGVEC_ERR_BAD_ARG, "out_ids cannot be produced with device_io");
+    if (o.device_io && o.formula != CGVEC_FORMULA_SIMD) return fail(CGVEC_ERR_UNSUPPORTED, "device_io supports the SIMD formula only");
+    if (nq == 0 || k == 0) {                                   // surreal_store.rs:62-64
+        if (out_counts && !o.device_io) for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+        return CGVEC_OK;
+    }
+    if (!queries) return fail(CGVEC_ERR_BAD_ARG, "queries is NULL");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const uint64_t n_total_hint = ix->n;                       // local rows; sharded ranks may be empty individually
+    if (ix->world == 1 && n_total_hint == 0) {
+        if (o.device_io) { if (out_counts) CUDA_TRY(cudaMemsetAsync(out_counts, 0, nq * sizeof(uint32_t), (cudaStream_t)o.stream)); }
+        else if (out_counts) for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+        return CGVEC_OK;
+    }
+    if (k > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u exceeds the fused top-k limit of %u", k, kMaxK);
+    if (ix->world > 1 && ix->n == 0) return fail(CGVEC_ERR_UNSUPPORTED, "a rank of a sharded index holds no rows");
+
+    SearchCtx* c = nullptr;
+    int rc = ctx_acquire(ix, &c);
+    if (rc) return rc;
+    cudaStream_t st = o.stream ? (cudaStream_t)o.stream : c->stream;
+    if (o.stream) cudaStreamWaitEvent(st, c->done, 0);         // scratch reuse across caller streams
+    const uint32_t qstride = (ix->dim + 3) & ~3u;
+    ix->searches++;
+
+    auto finish = [&](int code) { cudaEventRecord(c->done, st); ctx_release(ix, c); return code; };
+
+    if (o.device_io) {
+        if (qstride != ix->dim) return finish(fail(CGVEC_ERR_UNSUPPORTED, "device_io needs dim %% 4 == 0"));
+        uint32_t q0 = 0;
+        while (q0 < nq) {
+            uint32_t b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
+            rc = scan_batch(ix, c, queries + (size_t)q0 * qstride, b, k, o.metric, st, out_rows ? out_rows + (size_t)q0 * k : nullptr,
+                            out_scores ? out_scores + (size_t)q0 * k : nullptr, out_counts ? out_counts + q0 : nullptr);
+            if (rc) return finish(rc);
+            q0 += b;
+        }
+        return finish(CGVEC_OK);
+    }
+
+    // host I/O: stage queries through pinned memory, run, read results back
+    rc = ensure(&c->h_q, &c->hq_cap, (size_t)nq * qstride, true); if (rc) return finish(rc);
+    rc = ensure(&c->d_q, &c->q_cap, (size_t)nq * qstride); if (rc) return finish(rc);
+    for (uint32_t q = 0; q < nq; ++q) {
+        memcpy(c->h_q + (size_t)q * qstride, queries + (size_t)q * ix->dim, ix->dim * sizeof(float));
+        for (uint32_t i = ix->dim; i < qstride; ++i) c->h_q[(size_t)q * qstride + i] = 0.0f;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_q, c->h_q, (size_t)nq * qstride * sizeof(float), cudaMemcpyHostToDevice, st));
+    {
+        size_t oc = c->out_cap, oc2 = c->out_cap;
+        rc = ensure(&c->d_rows, &oc, (size_t)nq * k); if (rc) return finish(rc);
+        rc = ensure(&c->d_scores, &oc2, (size_t)nq * k); if (rc) return finish(rc);
+        c->out_cap = oc < oc2 ? oc : oc2;
+        rc = ensure(&c->d_counts, &c->cnt_cap, nq); if (rc) return finish(rc);
+        size_t hc = c->hout_cap, hc2 = c->hout_cap;
+        rc = ensure(&c->h_rows, &hc, (size_t)nq * k, true); if (rc) return finish(rc);
+        rc = ensure(&c->h_scores, &hc2, (size_t)nq * k, true); if (rc) return finish(rc);
+        c->hout_cap = hc < hc2 ? hc : hc2;
+        rc = ensure(&c->h_counts, &c->hcnt_cap, nq, true); if (rc) return finish(rc);
+    }
+    if (o.formula == CGVEC_FORMULA_SIMD) {
+        uint32_t q0 = 0;
+        while (q0 < nq) {
+            uint32_t b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
+            rc = scan_batch(ix, c, c->d_q + (size_t)q0 * qstride, b, k, o.metric, st, c->d_rows + (size_t)q0 * k, c->d_scores + (size_t)q0 * k,
+                            c->d_counts + q0);
+            if (rc) return finish(rc);
+            q0 += b;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->h_rows, c->d_rows, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(c->h_scores, c->d_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        if (ix->world > 1 || ix->row_offset != 0) return finish(fail(CGVEC_ERR_UNSUPPORTED, "non-SIMD formulas are not available on sharded indexes yet"));
+        for (uint32_t q = 0; q < nq; ++q) {
+            rc = search_formula(ix, c, c->d_q + (size_t)q * qstride, k, o.formula, st, c->h_rows + (size_t)q * k, c->h_scores + (size_t)q * k,
+                                c->h_counts + q);
+            if (rc) return finish(rc);
+        }
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+        uint32_t cnt = c->h_counts[q];
+        if (out_counts) out_counts[q] = cnt;
+        for (uint32_t i = 0; i < k; ++i) {
+            size_t o_i = (size_t)q * k + i;
+            bool valid = i < cnt;
+            uint64_t grow = valid ? c->h_rows[o_i] : ~0ull;
+            if (out_rows) out_rows[o_i] = grow;
+            if (out_scores) out_scores[o_i] = valid ? c->h_scores[o_i] : 0.0f;
+            if (out_ids) {
+                memset(out_ids[o_i], 0, 16);
+                if (valid && grow >= ix->row_offset && grow - ix->row_offset < ix->n && ix->has_id[grow - ix->row_offset])
+                    memcpy(out_ids[o_i], &ix->ids[(grow - ix->row_offset) * 16], 16);
+            }
+        }
+    }
+    return finish(CGVEC_OK);
+}
+
+CGVEC_EXPORT int cgvec_search(const cgvec_index* ix, const float* queries, uint32_t nq, uint32_t k, cgvec_metric metric,
+                              uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts) {
+    cgvec_search_opts o{};
+    o.struct_size = sizeof(o);
+    o.metric = metric;
+    o.formula = CGVEC_FORMULA_SIMD;
+    o.path = CGVEC_PATH_AUTO;
+    return cgvec_search_ex(ix, queries, nq, k, &o, out_rows, out_ids, out_scores, out_counts);
+}
+
+template <typename T>
+static void launch_rescore_t(Index* ix, const float* d_q, const uint64_t* d_local_rows, uint32_t n, int metric, int formula,
+                             float* d_out, cudaStream_t st) {
+    const int threads = 128;
+    unsigned blocks = (n * 8 + threads - 1) / threads;
+    rescore_kernel<T><<<blocks, threads, 0, st>>>(static_cast<const T*>(ix->d_rows), ix->dim, ix->ld, d_q, d_local_rows, n, metric, formula, d_out);
+    ix->launches++;
+}
+
+static int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st, uint64_t* h_rows,
+                          float* h_scores, uint32_t* h_count) {
+    const int ascending = (formula == CGVEC_FORMULA_BASELINE);
+    const uint64_t n = ix->n;
+    const uint32_t want = (uint32_t)(k < n ? k : n);
+    // |formula(x) - simd(x)| <= eps for every row: both evaluate the same cosine with <= (d+8) roundings of
+    // relative size 2^-24 each on the dot and on the norms (standard recursive-summation bound), so twice that.
+    const float eps = 4.0f * (float)(ix->dim + 8) * 5.9604645e-8f;
+    uint32_t kp = want + (want / 4 > 16 ? want / 4 : 16);
+    std::vector<uint64_t> cand_rows;
+    std::vector<float> cand_simd, cand_new;
+    while (true) {
+        if (kp > n) kp = (uint32_t)n;
+        if (kp > kMaxK) kp = kMaxK;
+        size_t oc = c->tmp_cap, oc2 = c->tmp_cap;
+        int rc = ensure(&c->d_tmp_rows, &oc, (size_t)kMaxK); if (rc) return rc;
+        rc = ensure(&c->d_tmp_scores, &oc2, (size_t)kMaxK * 2); if (rc) return rc;
+        c->tmp_cap = oc < oc2 ? oc : oc2;
+        size_t cc = c->cnt_cap;
+        rc = ensure(&c->d_counts, &cc, 4); if (rc) return rc;
+        c->cnt_cap = cc;
+        rc = scan_batch(ix, c, d_q, 1, kp, CGVEC_COSINE, st, c->d_tmp_rows, c->d_tmp_scores, c->d_counts);
+        if (rc) return rc;
+        // global -> local rows happen to coincide on an unsharded index (row_offset == 0 checked by caller path)
+        if (ix->dtype == CGVEC_F32) launch_rescore_t<float>(ix, d_q, c->d_tmp_rows, kp, CGVEC_COSINE, formula, c->d_tmp_scores + kMaxK, st);
+        else launch_rescore_t<__half>(ix, d_q, c->d_tmp_rows, kp, CGVEC_COSINE, formula, c->d_tmp_scores + kMaxK, st);
+        CUDA_TRY(cudaGetLastError());
+        cand_rows.resize(kp); cand_simd.resize(kp); cand_new.resize(kp);
+        CUDA_TRY(cudaMemcpyAsync(cand_rows.data(), c->d_tmp_rows, kp * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(cand_simd.data(), c->d_tmp_scores, kp * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(cand_new.data(), c->d_tmp_scores + kMaxK, kp * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        // re-rank the (<= 1024) candidates under the contract: a handful of comparisons, not a scoring path
+        std::vector<uint32_t> order(kp);
+        for (uint32_t i = 0; i < kp; ++i) order[i] = i;
+        auto better = [&](uint32_t a, uint32_t b) {
+            float x = cand_new[a], y = cand_new[b];
+            bool xn = std::isnan(x), yn = std::isnan(y);
+            if (xn != yn) return yn;
+            if (!xn && x != y) return ascending ? x < y : x > y;
+            return cand_rows[a] < cand_rows[b];
+        };
+        std::sort(order.begin(), order.end(), better);
+        bool proven = (kp >= n);
+        if (!proven) {
+            // rows outside the candidate set have simd score <= tau, hence formula score <= tau + eps
+            // (distance >= 1 - tau - eps for BASELINE).  NaN candidates make the bound meaningless -> widen.
+            float tau = cand_simd[kp - 1];
+            float kth = cand_new[order[want - 1]];
+            if (!std::isnan(tau) && !std::isnan(kth)) {
+                if (!ascending) proven = kth > tau + eps;
+                else proven = kth < (1.0f - tau) - eps;
+            }
+        }
+        if (proven || kp >= kMaxK) {
+            if (!proven) return fail(CGVEC_ERR_UNSUPPORTED, "could not separate the top-%u under formula %d within %u candidates", k, formula, kp);
+            for (uint32_t i = 0; i < want; ++i) { h_rows[i] = cand_rows[order[i]]; h_scores[i] = cand_new[order[i]]; }
+            *h_count = want;
+            return CGVEC_OK;
+        }
+        kp *= 2;
+    }
+}
+
+CGVEC_EXPORT int cgvec_row_of_id(const cgvec_index* ix, const uint8_t id[16], uint64_t* out_local_row) {
+    if (!ix || !id) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    auto it = ix->id2row.find(id_key(id));
+    if (it == ix->id2row.end()) return fail(CGVEC_ERR_NOT_FOUND, "id not present");
+    if (out_local_row) *out_local_row = it->second;
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_get_row(const cgvec_index* cix, uint64_t local_row, float* out_row) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || !out_row) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    if (local_row >= ix->n) return fail(CGVEC_ERR_NOT_FOUND, "row %llu out of range", (unsigned long long)local_row);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const uint8_t* src = static_cast<const uint8_t*>(ix->d_rows) + local_row * (size_t)ix->ld * ix->esize;
+    if (ix->dtype == CGVEC_F32) {
+        CUDA_TRY(cudaMemcpy(out_row, src, ix->dim * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        SearchCtx* c = nullptr;
+        int rc = ctx_acquire(ix, &c);
+        if (rc) return rc;
+        rc = ensure(&c->d_q, &c->q_cap, (size_t)ix->dim);
+        if (!rc) {
+            widen_row_kernel<<<(ix->dim + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const __half*>(src), ix->dim, c->d_q);
+            ix->launches++;
+            cudaError_t e = cudaMemcpyAsync(out_row, c->d_q, ix->dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = fail(CGVEC_ERR_CUDA, "row read-back failed: %s", cudaGetErrorString(e));
+        }
+        ctx_release(ix, c);
+        return rc;
+    }
+    return CGVEC_OK;
+}
+
+// Bulk read-back of rows [first, first+n) widened to f32 (row-major n x dim): snapshot / parity checks.
+CGVEC_EXPORT int cgvec_get_rows(const cgvec_index* cix, uint64_t first, uint64_t n, float* out) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (n == 0) return CGVEC_OK;
+    if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    if (first + n > ix->n) return fail(CGVEC_ERR_NOT_FOUND, "rows [%llu, %llu) out of range", (unsigned long long)first, (unsigned long long)(first + n));
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const size_t pitch = (size_t)ix->ld * ix->esize;
+    const uint8_t* src = static_cast<const uint8_t*>(ix->d_rows) + first * pitch;
+    if (ix->dtype == CGVEC_F32) {
+        CUDA_TRY(cudaMemcpy2D(out, (size_t)ix->dim * 4, src, pitch, (size_t)ix->dim * 4, n, cudaMemcpyDeviceToHost));
+        return CGVEC_OK;
+    }
+    std::vector<uint16_t> tmp((size_t)n * ix->dim);
+    CUDA_TRY(cudaMemcpy2D(tmp.data(), (size_t)ix->dim * 2, src, pitch, (size_t)ix->dim * 2, n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) out[i] = __half2float(__ushort_as_half(tmp[i]));   // exact widening of stored bits
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_get(const cgvec_index* ix, const uint8_t id[16], float* out_row) {
+    uint64_t row = 0;
+    int rc = cgvec_row_of_id(ix, id, &row);
+    if (rc) return rc;
+    return cgvec_get_row(ix, row, out_row);
+}
+
+CGVEC_EXPORT int cgvec_rescore(const cgvec_index* cix, const float* query, const uint64_t* local_rows, uint32_t n, cgvec_metric metric,
+                               cgvec_formula formula, float* out_scores) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (n == 0) return CGVEC_OK;
+    if (!query || !local_rows || !out_scores) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    if (formula != CGVEC_FORMULA_SIMD && metric == CGVEC_L2) return fail(CGVEC_ERR_UNSUPPORTED, "L2 exists in SIMD form only (simd_ops.rs:105-143)");
+    for (uint32_t i = 0; i < n; ++i)
+        if (local_rows[i] >= ix->n) return fail(CGVEC_ERR_NOT_FOUND, "row %llu out of range", (unsigned long long)local_rows[i]);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    SearchCtx* c = nullptr;
+    int rc = ctx_acquire(ix, &c);
+    if (rc) return rc;
+    auto done = [&](int code) { ctx_release(ix, c); return code; };
+    const uint32_t qstride = (ix->dim + 3) & ~3u;
+    rc = ensure(&c->d_q, &c->q_cap, (size_t)qstride); if (rc) return done(rc);
+    size_t oc = c->tmp_cap, oc2 = c->tmp_cap;
+    size_t need = n > kMaxK ? n : kMaxK;
+    rc = ensure(&c->d_tmp_rows, &oc, need); if (rc) return done(rc);
+    rc = ensure(&c->d_tmp_scores, &oc2, need * 2); if (rc) return done(rc);
+    c->tmp_cap = oc < oc2 ? oc : oc2;
+    cudaError_t e = cudaMemcpyAsync(c->d_q, query, ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_tmp_rows, local_rows, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e)));
+    if (ix->dtype == CGVEC_F32) launch_rescore_t<float>(ix, c->d_q, c->d_tmp_rows, n, metric, formula, c->d_tmp_scores, c->stream);
+    else launch_rescore_t<__half>(ix, c->d_q, c->d_tmp_rows, n, metric, formula, c->d_tmp_scores, c->stream);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, c->d_tmp_scores, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "rescore failed: %s", cudaGetErrorString(e)));
+    return done(CGVEC_OK);
+}
+
+CGVEC_EXPORT int cgvec_distances_first(const cgvec_index* cix, const float* query, uint64_t limit, float* out, uint64_t* out_n) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || !query) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    uint64_t m = limit < ix->n ? limit : ix->n;
+    if (out_n) *out_n = m;
+    if (m == 0) return CGVEC_OK;
+    if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    SearchCtx* c = nullptr;
+    int rc = ctx_acquire(ix, &c);
+    if (rc) return rc;
+    auto done = [&](int code) { ctx_release(ix, c); return code; };
+    rc = ensure(&c->d_q, &c->q_cap, (size_t)ix->dim + 4); if (rc) return done(rc);
+    float* d_out = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_out), m * sizeof(float));
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e)));
+    e = cudaMemcpyAsync(c->d_q, query, ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    const int threads = 128;
+    if (e == cudaSuccess) {
+        if (ix->dtype == CGVEC_F32) distances_first_kernel<float><<<(unsigned)((m + threads - 1) / threads), threads, 0, c->stream>>>(static_cast<const float*>(ix->d_rows), ix->dim, ix->ld, c->d_q, m, d_out);
+        else distances_first_kernel<__half><<<(unsigned)((m + threads - 1) / threads), threads, 0, c->stream>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, c->d_q, m, d_out);
+        ix->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "distances_first failed: %s", cudaGetErrorString(e)));
+    return done(CGVEC_OK);
+}
+
+// ================================================================================================
+// host-side helpers (pure CPU)
+// ================================================================================================
+CGVEC_EXPORT int cgvec_shard_range(uint64_t n, int world, int rank, uint64_t* begin, uint64_t* end) {
+    if (world < 1 || rank < 0 || rank >= world) return fail(CGVEC_ERR_BAD_ARG, "bad rank %d / world %d", rank, world);
+    uint64_t per = (n + (uint64_t)world - 1) / (uint64_t)world;   // GPU g owns [g*ceil(N/G), (g+1)*ceil(N/G))
+    uint64_t b = per * (uint64_t)rank, e = b + per;
+    if (b > n) b = n;
+    if (e > n) e = n;
+    if (begin) *begin = b;
+    if (end) *end = e;
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_merge_topk_host(const uint64_t* rows, const float* scores, const uint32_t* counts, uint32_t parts, uint32_t k,
+                                       int ascending, uint64_t* out_rows, float* out_scores, uint32_t* out_count) {
+    if ((!rows || !scores || !counts) && parts && k) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    std::vector<uint32_t> head(parts, 0);
+    auto better = [&](float x, uint64_t xr, float y, uint64_t yr) {
+        bool xn = std::isnan(x), yn = std::isnan(y);
+        if (xn != yn) return yn;
+        if (!xn && x != y) return ascending ? x < y : x > y;
+        return xr < yr;
+    };
+    uint32_t o = 0;
+    for (; o < k; ++o) {
+        int best = -1;
+        for (uint32_t p = 0; p < parts; ++p) {
+            if (head[p] >= counts[p] || head[p] >= k) continue;
+            size_t i = (size_t)p * k + head[p];
+            if (best < 0) { best = (int)p; continue; }
+            size_t j = (size_t)best * k + head[best];
+            if (better(scores[i], rows[i], scores[j], rows[j])) best = (int)p;
+        }
+        if (best < 0) break;
+        size_t j = (size_t)best * k + head[best]++;
+        if (out_rows) out_rows[o] = rows[j];
+        if (out_scores) out_scores[o] = scores[j];
+    }
+    if (out_count) *out_count = o;
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT uint64_t cgvec_prefetch_k_basic(uint64_t limit) {       // search.rs:113
+    uint64_t a = limit > UINT64_MAX / 3 ? UINT64_MAX : limit * 3, b = limit + 10;
+    return a > b ? a : b;
+}
+CGVEC_EXPORT uint64_t cgvec_prefetch_k_filtered(uint64_t limit) {    // search.rs:276
+    uint64_t a = limit > UINT64_MAX / 4 ? UINT64_MAX : limit * 4, b = limit + 25;
+    return a > b ? a : b;
+}
+CGVEC_EXPORT void cgvec_normalize_scores(float* s, size_t n) {       // search.rs:574-592
+    if (!s || n == 0) return;
+    float mn = INFINITY, mx = -INFINITY;
+    for (size_t i = 0; i < n; ++i) { if (s[i] < mn) mn = s[i]; if (s[i] > mx) mx = s[i]; }
+    float range = mx - mn;
+    if (!(range > 1e-12f)) range = 1e-12f;
+    for (size_t i = 0; i < n; ++i) s[i] = (s[i] - mn) / range;
+}
+
+// ================================================================================================
+// introspection
+// ================================================================================================
+CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || !out) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    drain_timings(ix);
+    memset(out, 0, sizeof(*out));
+    out->kernel_launches = ix->launches.load();
+    out->searches = ix->searches.load();
+    out->rows = ix->n;
+    out->bytes_resident = ix->n * (uint64_t)ix->ld * ix->esize + ix->n * sizeof(float);
+    out->sm_count = (uint32_t)ix->sm_count;
+    out->grid = ix->last_geom.grid;
+    out->block = kScanThreads;
+    out->smem_bytes = ix->last_geom.smem;
+    out->stages = ix->last_geom.stages;
+    out->tile_rows = ix->last_geom.tile_rows;
+    out->last_scan_ms = ix->last_scan_ms;
+    out->scan_ms_total = ix->scan_ms_total;
+    out->scans_timed = ix->scan_timed;
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t value) {
+    if (!ix || !key) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    std::string k(key);
+    if (k == "tile_rows") ix->opt_tile_rows = (int)value;
+    else if (k == "stages") ix->opt_stages = (int)value;
+    else if (k == "sync_interval") ix->opt_sync = (int)value;
+    else if (k == "l2_hint") ix->opt_l2_hint = (int)value;
+    else if (k == "grid") ix->opt_grid = (int)value;
+    else if (k == "timing") { ix->opt_timing = (int)value; if (!value) drain_timings(ix); }
+    else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; }
+    else if (k == "max_batch") ix->opt_max_nq = (int)value;
+    else return fail(CGVEC_ERR_BAD_ARG, "unknown option '%s'", key);
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT const char* cgvec_last_error(void) { return g_err; }
+CGVEC_EXPORT const char* cgvec_version(void) { return "cgvec_b200 0.1.0 (sm_100a)"; }

@@ -585,3 +585,40 @@ CG_API uint64_t cg_fair_top_k_search_mt(const float* q, const float* rows, uint6
     free(all); free(cnt); free(part);
     return r;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic inputs (bench / property tests): host twin of the device generator
+ * (codegraph-rust_b200/csrc/aux_kernels.cuh synth_value + normalize_avx2 arithmetic).  Not a reference
+ * function: it only produces the seeded inputs both sides consume.
+ * ------------------------------------------------------------------------------------------ */
+static inline float cg_synth_value(uint64_t seed, uint64_t row, uint32_t col) {
+    uint64_t z = seed ^ (row * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)col * 0xC2B2AE3D27D4EB4FULL);
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    int32_t s = (int32_t)(z & 0xffff) + (int32_t)((z >> 16) & 0xffff) + (int32_t)((z >> 32) & 0xffff) +
+                (int32_t)((z >> 48) & 0xffff) - 131070;
+    return (float)s * (1.0f / 65536.0f);
+}
+typedef struct { float* out; uint64_t first, n; size_t d; uint64_t seed; int unit_norm, f16; } cg_synth_ctx;
+static void cg_synth_job(int t, int T, void* a) {
+    cg_synth_ctx* c = (cg_synth_ctx*)a;
+    uint64_t blk = (c->n + T - 1) / T, lo = (uint64_t)t * blk, hi = lo + blk > c->n ? c->n : lo + blk;
+    for (uint64_t i = lo; i < hi; ++i) {
+        float* v = c->out + i * c->d;
+        for (size_t j = 0; j < c->d; ++j) v[j] = cg_synth_value(c->seed, c->first + i, (uint32_t)j);
+        if (c->unit_norm) {                                          /* simd_ops.rs:189-222 normalize_avx2 */
+            float nsq = cg_dot_product_avx2(v, v, c->d);
+            if (nsq != 0.0f) { float inv = 1.0f / sqrtf(nsq); for (size_t j = 0; j < c->d; ++j) v[j] = v[j] * inv; }
+        }
+        if (c->f16) for (size_t j = 0; j < c->d; ++j) v[j] = cg_half_to_float(cg_float_to_half(v[j]));
+    }
+}
+CG_API void cg_synth_rows(uint64_t seed, uint64_t first_row, uint64_t n, size_t d, int unit_norm, int round_f16,
+                          int threads, float* out) {
+    cg_synth_ctx c = {out, first_row, n, d, seed, unit_norm, round_f16};
+    int T = threads > 0 ? threads : cg_max_threads();
+    if ((uint64_t)T > n) T = n ? (int)n : 1;
+    cg_fork_join(T, cg_synth_job, &c);
+}

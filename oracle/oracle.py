@@ -63,6 +63,8 @@ def lib():
         L.cg_hash_text_embedding.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, fp]
         L.cg_widen_f16.restype = None; L.cg_widen_f16.argtypes = [u16p, C.c_uint64, fp]
         L.cg_narrow_f16.restype = None; L.cg_narrow_f16.argtypes = [fp, C.c_uint64, u16p]
+        L.cg_synth_rows.restype = None
+        L.cg_synth_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, fp]
         L.cg_vecs_create.restype = C.c_void_p; L.cg_vecs_create.argtypes = [fp, C.c_uint64, C.c_size_t]
         L.cg_vecs_destroy.restype = None; L.cg_vecs_destroy.argtypes = [C.c_void_p]
         L.cg_max_threads.restype = C.c_int
@@ -261,3 +263,10 @@ def fair_top_k_mt(query, rows, k, threads=0):
 
 def max_threads():
     return int(lib().cg_max_threads())
+
+
+def synth_rows(seed, first_row, n, d, unit_norm=True, f16=False, threads=0):
+    """Host twin of cgvec_fill_synthetic (rows first_row .. first_row+n)."""
+    out = np.empty((n, d), np.float32)
+    lib().cg_synth_rows(seed, first_row, n, d, 1 if unit_norm else 0, 1 if f16 else 0, threads, _fp(out))
+    return out

@@ -1,0 +1,142 @@
+"""CPU-side checks (no GPU needed): the C-ABI library loads and exports every symbol include/cgvec.h
+declares, fails loudly (no CPU fallback) without a device, and its host-side helpers agree with the oracle."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(cg):
+    lib = cg.load_library()
+    hdr = open(os.path.join(ROOT, "include", "cgvec.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cgvec_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    assert declared == set(cg.EXPORTS), declared ^ set(cg.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", cg.lib_path()], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (cgvec_[a-z0-9_]+)", out))
+    assert declared <= exported
+    # nothing but the ABI leaks out of the shared object
+    leaked = [l for l in out.splitlines() if " T " in l and "cgvec_" not in l]
+    assert not leaked, leaked[:5]
+
+
+def test_library_is_sm100a_native(cg):
+    """The scan kernel must carry the TMA-engine bulk copy (SASS UBLKCP) and mbarrier ops — not a generic build."""
+    out = subprocess.run(["cuobjdump", "-sass", cg.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    assert "UBLKCP" in out.stdout and "SYNCS" in out.stdout
+
+
+@pytest.mark.skipif(_has_gpu(), reason="this container check only applies without a GPU")
+def test_no_cpu_fallback_without_device(cg):
+    with pytest.raises(cg.CgvecError) as ei:
+        cg.Index(768)
+    assert ei.value.code == cg.ERR_NO_DEVICE
+    assert "no CPU fallback" in ei.value.msg
+    with pytest.raises(cg.CgvecError):
+        cg.ParallelVectorOps.parallel_top_k_search(np.ones(8, np.float32), np.ones((4, 8), np.float32), 2)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "codegraph-rust_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".rs")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "cgvec_oracle" not in txt, f
+    out = subprocess.run(["ldd", os.path.join(pkg, "libcgvec_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_argument_validation_never_aborts(cg):
+    import ctypes as C
+    lib = cg.load_library()
+    h = C.c_void_p()
+    assert lib.cgvec_create(0, 0, None, 1, C.byref(h)) == cg.ERR_BAD_DIM
+    assert lib.cgvec_create(8, 7, None, 1, C.byref(h)) == cg.ERR_BAD_ARG
+    assert lib.cgvec_create(8, 0, None, 0, C.byref(h)) == cg.ERR_BAD_ARG
+    assert lib.cgvec_create(8, 0, None, 1, None) == cg.ERR_BAD_ARG
+    assert lib.cgvec_add(None, None, None, 5) == cg.ERR_BAD_ARG
+    assert lib.cgvec_search(None, None, 1, 1, 0, None, None, None, None) == cg.ERR_BAD_ARG
+    assert lib.cgvec_destroy(None) == 0
+    assert lib.cgvec_len(None) == 0
+    assert lib.cgvec_create_rank(8, 0, 0, 2, 2, None, 0, C.byref(h)) == cg.ERR_BAD_ARG
+    assert b"rank" in lib.cgvec_last_error()
+
+
+def test_shard_range_covers_and_partitions(cg):
+    for n in (0, 1, 7, 8, 9, 1000, 10**6 + 3):
+        for world in (1, 2, 3, 4, 8):
+            spans = [cg.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            per = -(-n // world)
+            assert all(e - b <= per for b, e in spans)
+
+
+def test_prefetch_and_normalise_match_oracle(cg, oracle):
+    for lim in (0, 1, 3, 5, 10, 100, 1000):
+        assert cg.prefetch_k_basic(lim) == oracle.prefetch_k_basic(lim)
+        assert cg.prefetch_k_filtered(lim) == oracle.prefetch_k_filtered(lim)
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 17):
+        s = rng.standard_normal(n).astype(np.float32)
+        assert cg.normalize_scores(s).tobytes() == oracle.normalize_scores(s).tobytes()
+    assert cg.normalize_scores(np.float32([0.25, 0.25])).tolist() == [0.0, 0.0]
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_merge_topk_host_equals_global_topk(cg, oracle, metric):
+    """Top-k of a union == merge of per-shard top-k, incl. ties across shards and short shards."""
+    rng = np.random.default_rng(4)
+    n, d, k, world = 1000, 48, 20, 3
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[500] = rows[10]; rows[900] = rows[10]          # exact ties across shards
+    q = rows[10] + 0.01 * rng.standard_normal(d).astype(np.float32)
+    m = oracle.COSINE if metric == "cosine" else oracle.L2
+    want_idx, want_sc = oracle.parallel_top_k_search(q, rows, k, metric=m)
+    prow = np.zeros((world, k), np.uint64); psc = np.zeros((world, k), np.float32); pcnt = np.zeros(world, np.uint32)
+    for r in range(world):
+        b, e = cg.shard_range(n, world, r)
+        idx, sc = oracle.parallel_top_k_search(q, rows[b:e], k, metric=m)
+        prow[r, :len(idx)] = idx + b; psc[r, :len(idx)] = sc; pcnt[r] = len(idx)
+    got_idx, got_sc = cg.merge_topk_host(prow, psc, pcnt, k, ascending=(metric == "l2"))
+    assert got_idx.tolist() == want_idx.tolist()
+    assert got_sc.tobytes() == want_sc.tobytes()
+    # a shard with fewer than k rows
+    pcnt2 = pcnt.copy(); pcnt2[2] = 3
+    got2, _ = cg.merge_topk_host(prow, psc, pcnt2, k, ascending=(metric == "l2"))
+    assert len(got2) == k
+
+
+def test_synth_mirror_properties():
+    """tests/synth.py is the host twin of the device generator: check its own invariants here (the GPU
+    test checks device == mirror bit for bit)."""
+    from tests import synth
+    x = synth.synth_rows(0xC0DE6A9F, np.arange(64), 768, unit_norm=True)
+    assert x.dtype == np.float32 and x.shape == (64, 768)
+    n = np.linalg.norm(x.astype(np.float64), axis=1)
+    assert np.all(np.abs(n - 1) < 1e-6)
+    raw = synth.synth_raw(1, np.arange(2000), 64)
+    assert abs(float(raw.mean())) < 0.01 and 0.5 < float(raw.std()) < 0.65
+    assert synth.synth_raw(1, [5], 8).tobytes() == synth.synth_raw(1, [5], 8).tobytes()
+    assert synth.synth_raw(1, [5], 8).tobytes() != synth.synth_raw(2, [5], 8).tobytes()

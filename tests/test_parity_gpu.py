@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bar: indices bit-exact; SIMD-formula scores bit-identical (stricter than north_star's 1e-5 relative)."""
+import uuid
+
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5      # north_star's tolerance for fp32 distances; SIMD-formula scores are checked bit-for-bit instead
+
+
+def _metric(cg, oracle, name):
+    return {"cosine": (cg.COSINE, oracle.COSINE), "dot": (cg.DOT, oracle.DOT), "l2": (cg.L2, oracle.L2)}[name]
+
+
+def _check_exact(cg, oracle, rows, queries, k, metric="cosine", dtype=None):
+    dtype = cg.F32 if dtype is None else dtype
+    gm, om = _metric(cg, oracle, metric)
+    ix = cg.Index(rows.shape[1], dtype)
+    try:
+        ix.add(rows)
+        ref_rows = rows if dtype == cg.F32 else rows.astype(np.float16).astype(np.float32)
+        got_r, got_s, cnt = ix.search(queries, k, gm)
+        q2 = np.atleast_2d(queries)
+        for qi in range(q2.shape[0]):
+            wi, ws = oracle.parallel_top_k_search(q2[qi], ref_rows, k, metric=om)
+            assert int(cnt[qi]) == len(wi) == min(k, rows.shape[0])
+            assert got_r[qi, :len(wi)].tolist() == wi.tolist(), (metric, qi, got_r[qi, :len(wi)], wi)
+            assert np.array_equal(got_s[qi, :len(wi)], ws, equal_nan=True), (metric, qi, got_s[qi, :len(wi)], ws)
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("d", [1, 7, 8, 24, 31, 32, 33, 100, 384, 768, 1024, 1027])
+def test_dimensions_incl_ragged_tails(cg, oracle, d):
+    """adaptive_cosine_similarity switches at len 32 (simd_ops.rs:284); d % 8 != 0 exercises the scalar tail (:59-65)."""
+    rng = np.random.default_rng(d)
+    rows = rng.standard_normal((1500, d)).astype(np.float32)
+    q = rng.standard_normal(d).astype(np.float32)
+    for metric in ("cosine", "dot", "l2"):
+        _check_exact(cg, oracle, rows, q, 10, metric)
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (1, 10), (3, 10), (17, 17), (33, 5), (1000, 1), (1000, 100), (5000, 1024), (20000, 10)])
+def test_row_counts_and_k(cg, oracle, n, k):
+    rng = np.random.default_rng(n * 31 + k)
+    rows = rng.standard_normal((n, 64)).astype(np.float32)
+    q = rng.standard_normal(64).astype(np.float32)
+    _check_exact(cg, oracle, rows, q, k, "cosine")
+
+
+def test_reference_test_parallel_operations(cg, oracle):
+    """simd_ops.rs:461-472: q=[1.0;256], row_i[j]=i+j, N=1000, k=10 -> forced answer [999..990]."""
+    q = np.ones(256, np.float32)
+    rows = (np.arange(1000)[:, None] + np.arange(256)[None, :]).astype(np.float32)
+    res = cg.ParallelVectorOps.parallel_top_k_search(q, rows, 10)
+    assert len(res) == 10
+    assert [i for i, _ in res] == list(range(999, 989, -1))
+    wi, ws = oracle.parallel_top_k_search(q, rows, 10)
+    assert np.array_equal(np.float32([s for _, s in res]), ws)
+
+
+def test_config1_10k_x_768(cg, oracle):
+    """BASELINE config 1: 10k x 768 f32, 1 query, top-10 cosine."""
+    rows = synth.synth_rows(0xC0DE6A9F, np.arange(10_000), 768)
+    q = synth.synth_rows(0x5EED0001, [0], 768)[0]
+    _check_exact(cg, oracle, rows, q, 10, "cosine")
+
+
+@pytest.mark.parametrize("nq", [1, 2, 3, 4, 5, 7, 9])
+def test_query_batches(cg, oracle, nq):
+    rng = np.random.default_rng(nq)
+    rows = rng.standard_normal((3000, 96)).astype(np.float32)
+    qs = rng.standard_normal((nq, 96)).astype(np.float32)
+    for metric in ("cosine", "l2"):
+        _check_exact(cg, oracle, rows, qs, 12, metric)
+
+
+@pytest.mark.parametrize("d", [64, 768, 1000])
+def test_fp16_storage_oracle_is_widened_rows(cg, oracle, d):
+    rng = np.random.default_rng(d + 1)
+    rows = (rng.standard_normal((4000, d)) / np.sqrt(d)).astype(np.float32)
+    qs = rng.standard_normal((2, d)).astype(np.float32)
+    for metric in ("cosine", "dot", "l2"):
+        _check_exact(cg, oracle, rows, qs, 10, metric, dtype=cg.F16)
+
+
+def test_tie_nan_zero_contract(cg, oracle):
+    """ties -> lower row; NaN last; zero-norm row -> 0.0; k > N -> N; k == 0 -> empty."""
+    rows = np.zeros((6, 32), np.float32)
+    rows[:, 0] = 1.0
+    rows[4] = 0.0
+    rows[2, 1] = np.nan
+    q = np.zeros(32, np.float32); q[0] = 1.0
+    ix = cg.Index(32)
+    ix.add(rows)
+    r, s, c = ix.search(q, 10)
+    assert int(c[0]) == 6
+    assert r[0, :6].tolist() == [0, 1, 3, 5, 4, 2]
+    assert np.isnan(s[0, 5]) and s[0, 4] == 0.0
+    wi, ws = oracle.parallel_top_k_search(q, rows, 10)
+    assert r[0, :6].tolist() == wi.tolist() and np.array_equal(s[0, :6], ws, equal_nan=True)
+    r0, s0, c0 = ix.search(q, 0)
+    assert int(c0[0]) == 0
+    # zero query -> every score 0.0 -> rows in index order
+    r1, s1, c1 = ix.search(np.zeros(32, np.float32), 3)
+    assert r1[0].tolist() == [0, 1, 3] or r1[0].tolist() == oracle.parallel_top_k_search(np.zeros(32, np.float32), rows, 3)[0].tolist()
+    ix.close()
+
+
+def test_many_exact_ties_across_ctas(cg, oracle):
+    """Duplicate rows everywhere: the k winners must be the k lowest row indices among equals."""
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((4, 128)).astype(np.float32)
+    rows = np.repeat(base, 5000, axis=0)[rng.permutation(20000)]
+    q = base[1]
+    _check_exact(cg, oracle, rows, q, 64, "cosine")
+    _check_exact(cg, oracle, rows, q, 64, "l2")
+
+
+def test_formulas_rescore_bit_exact(cg, oracle):
+    """cgvec_rescore reproduces each reference formula bit-for-bit (simd_ops.rs:257-278, search.rs:519-533,
+    optimization.rs:404-418)."""
+    rng = np.random.default_rng(8)
+    rows = rng.standard_normal((300, 200)).astype(np.float32)
+    rows[7] = 0.0
+    q = rng.standard_normal(200).astype(np.float32)
+    ix = cg.Index(200)
+    ix.add(rows)
+    sel = np.arange(300, dtype=np.uint64)
+    got = ix.rescore(q, sel, cg.COSINE, cg.FORMULA_SCALAR)
+    assert got.tobytes() == np.float32([oracle.cosine_similarity_scalar(q, r) for r in rows]).tobytes()
+    got = ix.rescore(q, sel, cg.COSINE, cg.FORMULA_SEQ)
+    assert got.tobytes() == np.float32([oracle.cosine_similarity_seq(q, r) for r in rows]).tobytes()
+    got = ix.rescore(q, sel, cg.COSINE, cg.FORMULA_BASELINE)
+    assert got.tobytes() == np.float32([oracle.cosine_distance_seq(q, r) for r in rows]).tobytes()
+    got = ix.rescore(q, sel, cg.COSINE, cg.FORMULA_SIMD)
+    assert got.tobytes() == oracle.scores(q, rows).tobytes()
+    got = ix.rescore(q, sel, cg.L2, cg.FORMULA_SIMD)
+    assert got.tobytes() == oracle.scores(q, rows, metric=oracle.L2).tobytes()
+    ix.close()
+
+
+def test_search_baseline_formula_on_reference_vectors(cg, oracle):
+    """model_optimization_tests.rs:36-58,383-424 vectors (N=1000, d=128, seed 11223, query=row 0):
+    formula BASELINE == ModelOptimizer::search_baseline (optimization.rs:376-402): same indices, same distances."""
+    vecs = oracle.generate_optimization_vectors(1000, 128, 11223)
+    q = vecs[0]
+    want_i, want_d = oracle.search_baseline(q, vecs, 10)
+    ix = cg.Index(128)
+    ix.add(vecs)
+    r, s, c = ix.search(q, 10, cg.COSINE, formula=cg.FORMULA_BASELINE)
+    assert int(c[0]) == 10 and r[0, 0] == 0
+    assert r[0].tolist() == want_i.tolist()
+    assert s[0].tobytes() == want_d.tobytes()
+    # and the trait-level semantics of InMemoryVectorStore (graph_vector.rs:479-494) via formula SEQ
+    wi, ws = oracle.inmemory_search_similar(q, vecs, 25)
+    r2, s2, _ = ix.search(q, 25, cg.COSINE, formula=cg.FORMULA_SEQ)
+    assert r2[0].tolist() == wi.tolist() and s2[0].tobytes() == ws.tobytes()
+    ix.close()
+
+
+def test_vector_store_trait_mirror(cg, oracle):
+    """trait VectorStore round trip (traits.rs:11-16) incl. skip-None, upsert-by-id and get_embedding -> None."""
+    rng = np.random.default_rng(12)
+    embs = rng.standard_normal((200, 384)).astype(np.float32)
+    nodes = [cg.CodeNode(uuid.UUID(int=i + 1), embs[i].tolist()) for i in range(200)]
+    nodes.insert(50, cg.CodeNode(uuid.UUID(int=10_000), None))                 # no embedding -> skipped
+    store = cg.B200VectorStore(384)
+    store.store_embeddings(nodes)
+    assert len(store.index) == 200
+    q = embs[17] + 0.05 * rng.standard_normal(384).astype(np.float32)
+    ids = store.search_similar(q, 5)
+    wi, _ = oracle.parallel_top_k_search(q, embs, 5)
+    assert [i.int - 1 for i in ids] == wi.tolist()
+    assert ids[0] == uuid.UUID(int=18)
+    assert store.search_similar(q, 0) == [] and store.search_similar([], 5) == []
+    assert store.get_embedding(uuid.UUID(int=999_999)) is None
+    assert np.float32(store.get_embedding(uuid.UUID(int=18))).tobytes() == embs[17].tobytes()
+    # upsert: same id, new embedding -> overwritten in place, still 200 rows
+    store.store_embeddings([cg.CodeNode(uuid.UUID(int=18), (-embs[17]).tolist())])
+    assert len(store.index) == 200
+    assert store.search_similar(q, 1)[0] != uuid.UUID(int=18)
+    # backend seam: ("nodes:<uuid>", cosine distance) ascending
+    be = cg.B200Backend(store)
+    knn = be.vector_knn("embedding_384", q, 4, 100)
+    assert be.last_column == "embedding_384" and len(knn) == 4
+    assert all(k.startswith("nodes:") for k, _ in knn)
+    assert [d for _, d in knn] == sorted(d for _, d in knn)
+
+
+def test_semantic_search_by_embedding_mirror(cg, oracle):
+    """search.rs:91-144: over-fetch max(3k, k+10), exact rescore, stable sort, truncate, min-max normalise."""
+    rng = np.random.default_rng(13)
+    embs = rng.standard_normal((500, 128)).astype(np.float32)
+    store = cg.B200VectorStore(128)
+    store.store_embeddings([cg.CodeNode(uuid.UUID(int=i + 1), embs[i]) for i in range(500)])
+    q = rng.standard_normal(128).astype(np.float32)
+    res = cg.SemanticSearch(store).search_by_embedding(q, 7)
+    wi, wnorm, _ = oracle.search_by_embedding(q, embs, 7)
+    assert [r.node_id.int - 1 for r in res] == wi.tolist()
+    assert np.float32([r.score for r in res]).tobytes() == wnorm.tobytes()
+    assert res[0].score == 1.0 and res[-1].score == 0.0
+
+
+def test_gpu_acceleration_api_mirror(cg, oracle):
+    """gpu.rs:221-322: upload_vectors(flat, dim) + compute_distances == compute_distances_cpu (first `limit` rows)."""
+    rng = np.random.default_rng(14)
+    flat = rng.standard_normal(40 * 96).astype(np.float32)
+    q = rng.standard_normal(96).astype(np.float32)
+    gpu = cg.GpuAcceleration()
+    data = gpu.upload_vectors(flat, 96)
+    got = gpu.compute_distances(q, data, 25)
+    assert got.tobytes() == oracle.compute_distances_cpu(q, flat, 96, 25).tobytes()
+    assert len(gpu.compute_distances(q, data, 1000)) == 40
+    with pytest.raises(cg.CgvecError):
+        gpu.upload_vectors(flat[:-1], 96)
+    with pytest.raises(cg.CgvecError):
+        gpu.compute_distances(q[:10], data, 5)
+
+
+def test_normalize_rows_matches_normalize_avx2(cg, oracle):
+    """parallel_normalize_vectors (simd_ops.rs:386-419) -> normalize_avx2 (:189-222), bit-exact, zero rows untouched."""
+    rng = np.random.default_rng(15)
+    rows = (rng.standard_normal((100, 77)) * 3).astype(np.float32)
+    rows[5] = 0.0
+    ix = cg.Index(77)
+    ix.add(rows)
+    ix.normalize_rows()
+    got = ix.get_rows(0, 100)
+    want = np.stack([oracle.normalize_avx2(r) for r in rows])
+    assert got.tobytes() == want.tobytes()
+    ix.close()
+
+
+def test_device_synthetic_rows_equal_host_mirror(cg):
+    for dtype, f16 in ((cg.F32, False), (cg.F16, True)):
+        ix = cg.Index(768, dtype)
+        ix.fill_synthetic(3000, 0xC0DE6A9F, True)
+        got = ix.get_rows(0, 3000)
+        want = synth.synth_rows(0xC0DE6A9F, np.arange(3000), 768, True, f16)
+        assert got.tobytes() == want.tobytes()
+        ix.close()
+
+
+def test_errors_cross_the_boundary_as_codes(cg):
+    ix = cg.Index(16)
+    with pytest.raises(cg.CgvecError) as e:
+        ix.add(np.zeros((3, 15), np.float32))
+    assert e.value.code == cg.ERR_BAD_DIM
+    with pytest.raises(cg.CgvecError) as e:
+        ix.search(np.zeros(17, np.float32), 3)
+    assert e.value.code == cg.ERR_BAD_DIM
+    r, s, c = ix.search(np.zeros(16, np.float32), 3)      # empty index -> empty result, not an error
+    assert int(c[0]) == 0
+    ix.add(np.ones((4, 16), np.float32))
+    with pytest.raises(cg.CgvecError) as e:
+        ix.search(np.ones(16, np.float32), 5000)
+    assert e.value.code == cg.ERR_UNSUPPORTED
+    assert ix.get_row(2).tolist() == [1.0] * 16
+    with pytest.raises(cg.CgvecError):
+        ix.get_row(99)
+    ix.close()
+
+
+def test_concurrent_searches_are_reentrant(cg, oracle):
+    """multi_vector_search fans out concurrent &self calls (search.rs:358-361)."""
+    import threading
+    rng = np.random.default_rng(16)
+    rows = rng.standard_normal((20000, 64)).astype(np.float32)
+    qs = rng.standard_normal((16, 64)).astype(np.float32)
+    ix = cg.Index(64)
+    ix.add(rows)
+    want = [oracle.parallel_top_k_search(q, rows, 10)[0].tolist() for q in qs]
+    got = [None] * 16
+
+    def work(i):
+        for _ in range(5):
+            got[i] = ix.search(qs[i], 10)[0][0].tolist()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(16)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert got == want
+    ix.close()
+
+
+def test_config2_full_size_1m_x_768(cg, oracle):
+    """BASELINE config 2 at full size: 1M x 768 f32, batch-1, top-10, checked against the oracle on the rows
+    read back from HBM; plus size-independent properties (planted neighbour, self-match, idempotence)."""
+    n, d = 1_000_000, 768
+    ix = cg.Index(d)
+    ix.fill_synthetic(n, 0xC0DE6A9F, True)
+    assert len(ix) == n
+    rows = ix.get_rows(0, n)
+    q = synth.synth_rows(0x5EED0001, [0], d)[0]
+    r, s, c = ix.search(q, 10)
+    wi, ws = oracle.parallel_top_k_search(q, rows, 10)
+    assert r[0].tolist() == wi.tolist()
+    assert s[0].tobytes() == ws.tobytes()
+    r2, s2, _ = ix.search(q, 10)
+    assert r2.tobytes() == r.tobytes() and s2.tobytes() == s.tobytes()          # idempotent
+    rng = np.random.default_rng(99)
+    for planted in (0, 123_456, n - 1):
+        pq = rows[planted] + np.float32(0.05 / np.sqrt(d)) * rng.standard_normal(d).astype(np.float32)
+        rr, ss, _ = ix.search(pq, 5)
+        assert rr[0, 0] == planted and ss[0, 0] > 0.99
+        rr, ss, _ = ix.search(rows[planted], 1, cg.L2)
+        assert rr[0, 0] == planted and ss[0, 0] == 0.0
+    # dot and L2 at full size against the oracle too
+    for gm, om in ((cg.DOT, oracle.DOT), (cg.L2, oracle.L2)):
+        r, s, _ = ix.search(q, 10, gm)
+        wi, ws = oracle.parallel_top_k_search(q, rows, 10, metric=om)
+        assert r[0].tolist() == wi.tolist() and s[0].tobytes() == ws.tobytes()
+    st = ix.stats()
+    assert st.grid == st.sm_count
+    ix.close()
