@@ -59,7 +59,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("searches", C.c_uint64), ("rows", C.c_uint64),
                 ("bytes_resident", C.c_uint64), ("sm_count", C.c_uint32), ("grid", C.c_uint32), ("block", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("stages", C.c_uint32), ("tile_rows", C.c_uint32),
-                ("last_scan_ms", C.c_float), ("scan_ms_total", C.c_double), ("scans_timed", C.c_uint64)]
+                ("last_scan_ms", C.c_float), ("scan_ms_total", C.c_double), ("scans_timed", C.c_uint64),
+                ("tc_batches", C.c_uint64), ("tc_fallbacks", C.c_uint64)]
 
 
 _lib = None

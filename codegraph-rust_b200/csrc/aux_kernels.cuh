@@ -151,22 +151,23 @@ __global__ void make_keys_kernel(const float* __restrict__ scores, const uint64_
 }
 
 // ---- K5 -------------------------------------------------------------------------------------------
-// in  : [nq][n_lists][k] keys (each list sorted or not — the CTA sorts), 0 = empty
-// out : [nq][n_out][k]   where CTA (x, y) merges lists [x*lists_per_cta, ...) of query y.
+// in  : [nq][n_lists][list_len] keys (each list sorted or not — the CTA sorts), 0 = empty
+// out : [nq][n_out][k]   where CTA (x, y) merges lists [x*lists_per_cta, ...) of query y and keeps the best k.
 // When out_rows/out_scores/out_counts are given (final level, n_out == 1) the winners are decoded too.
 constexpr int kMergeThreads = 256;
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_t* __restrict__ in, uint32_t n_lists,
-                                                                    uint32_t k, uint32_t lists_per_cta, uint32_t sort_n,
-                                                                    uint64_t* __restrict__ out, int ascending,
+                                                                    uint32_t list_len, uint32_t k, uint32_t lists_per_cta,
+                                                                    uint32_t sort_n, uint64_t* __restrict__ out, int ascending,
                                                                     uint64_t* __restrict__ out_rows,
                                                                     float* __restrict__ out_scores,
                                                                     uint32_t* __restrict__ out_counts) {
-    extern __shared__ __align__(16) uint64_t s_keys[];
+    extern __shared__ __align__(16) uint64_t s_merge_keys[];
+    uint64_t* s_keys = s_merge_keys;
     const uint32_t q = blockIdx.y, n_out = gridDim.x;
     const uint32_t first = blockIdx.x * lists_per_cta;
     const uint32_t lists = min(lists_per_cta, n_lists - first);
-    const uint64_t* src = in + ((size_t)q * n_lists + first) * k;
-    const uint32_t total = lists * k;
+    const uint64_t* src = in + ((size_t)q * n_lists + first) * list_len;
+    const uint32_t total = lists * list_len;
     for (uint32_t i = threadIdx.x; i < sort_n; i += kMergeThreads) s_keys[i] = (i < total) ? src[i] : 0ull;
     __syncthreads();
     bitonic_sort_desc(s_keys, sort_n, threadIdx.x, kMergeThreads, 0);

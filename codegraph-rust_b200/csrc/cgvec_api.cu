@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "nccl_dyn.h"
 #include "scan_exact.cuh"
+#include "scan_tc.cuh"
 
 #define CGVEC_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -90,12 +91,19 @@ struct SearchCtx {
     uint64_t* d_gather = nullptr; size_t gather_cap = 0;  // keys
     uint64_t* d_rows = nullptr;  float* d_scores = nullptr; uint32_t* d_counts = nullptr; size_t out_cap = 0, cnt_cap = 0;
     uint64_t* d_tmp_rows = nullptr; float* d_tmp_scores = nullptr; size_t tmp_cap = 0;
+    // tensor path (scan_tc.cuh)
+    __half* d_B = nullptr;       size_t B_cap = 0;
+    float* d_tc_f = nullptr;     size_t tcf_cap = 0;      // thr[N] | na[N] | rho[N]
+    uint32_t* d_tc_u = nullptr;  size_t tcu_cap = 0;      // count[N] | proven[N] | overflow
+    uint64_t* d_cand = nullptr;  size_t cand_cap = 0;     // [N][cap]
+    uint64_t* d_exact = nullptr; size_t exact_cap = 0;    // [N][kp] exact keys
+    uint32_t* h_proven = nullptr; size_t hprov_cap = 0;
     float* h_q = nullptr;        size_t hq_cap = 0;
     uint64_t* h_rows = nullptr;  float* h_scores = nullptr; uint32_t* h_counts = nullptr; size_t hout_cap = 0, hcnt_cap = 0;
 };
 
 struct ScanGeom {
-    uint32_t tile_rows, stages, sync_interval, cand_cap, row_words, grid, smem;
+    uint32_t tile_rows, stages, groups, sync_interval, cand_cap, row_words, grid, smem;
 };
 
 struct Index {
@@ -123,6 +131,8 @@ struct Index {
 
     // knobs (cgvec_set_option)
     int opt_tile_rows = 0, opt_stages = 0, opt_sync = 0, opt_l2_hint = 0, opt_grid = 0, opt_timing = 0, opt_max_nq = kScanMaxQ;
+    int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0;
+    std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
 
     // stats
     std::atomic<uint64_t> launches{0}, searches{0};
@@ -181,6 +191,7 @@ void ctx_release(Index* ix, SearchCtx* c) {
 void ctx_free(SearchCtx* c) {
     cudaFree(c->d_q); cudaFree(c->d_part[0]); cudaFree(c->d_part[1]); cudaFree(c->d_gather);
     cudaFree(c->d_rows); cudaFree(c->d_scores); cudaFree(c->d_counts); cudaFree(c->d_tmp_rows); cudaFree(c->d_tmp_scores);
+    cudaFree(c->d_B); cudaFree(c->d_tc_f); cudaFree(c->d_tc_u); cudaFree(c->d_cand); cudaFree(c->d_exact); cudaFreeHost(c->h_proven);
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_rows); cudaFreeHost(c->h_scores); cudaFreeHost(c->h_counts);
     if (c->done) cudaEventDestroy(c->done);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -242,30 +253,40 @@ int launch_norms(Index* ix, uint64_t first, uint64_t count, cudaStream_t st) {
 // ---- scan planning / launch ---------------------------------------------------------------------
 int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
     g->row_words = scan_row_words(ix->ld, ix->esize);
-    const uint32_t try_tiles[4] = {16, 8, 4, 32};
+    const uint32_t try_tiles[4] = {16, 32, 8, 4};
+    uint32_t best_bytes = 0;
     for (int t = 0; t < 4; ++t) {
         uint32_t tile = ix->opt_tile_rows ? (uint32_t)ix->opt_tile_rows : try_tiles[t];
         if (tile != 4 && tile != 8 && tile != 16 && tile != 32) return fail(CGVEC_ERR_BAD_ARG, "tile_rows must be 4, 8, 16 or 32");
-        uint32_t ngroups = kScanConsumerWarps / (tile / 4);
-        uint32_t sync = ix->opt_sync ? (uint32_t)ix->opt_sync : 8;
-        sync = ((sync + ngroups - 1) / ngroups) * ngroups;
-        uint32_t cand = next_pow2(k + sync * tile);
-        if (cand < 64) cand = 64;
+        const uint32_t gmax = kScanConsumerWarps / (tile / 4);
         uint32_t max_stages = ix->opt_stages ? (uint32_t)ix->opt_stages : 8;
         for (uint32_t s = max_stages; s >= 2; --s) {
+            // A stage must always be drained by the same warp group, otherwise a group would wait on a phase of the
+            // stage's mbarrier without having observed the previous one (parity aliasing): active groups divide stages.
+            uint32_t groups = 1;
+            for (uint32_t a = gmax; a >= 1; --a) if (s % a == 0) { groups = a; break; }
+            if (ix->opt_stages == 0 && groups < gmax && groups * 2 <= gmax && s > 2) continue;   // prefer well-populated groupings
+            uint32_t sync = ix->opt_sync ? (uint32_t)ix->opt_sync : 8;
+            sync = ((sync + groups - 1) / groups) * groups;
+            uint32_t cand = next_pow2(k + sync * tile);
+            if (cand < 64) cand = 64;
             ScanSmemLayout L = scan_smem_layout(g->row_words, tile, s, ix->dim, nq, cand);
-            if (L.total <= kSmemBudget) {
-                g->tile_rows = tile; g->stages = s; g->sync_interval = sync; g->cand_cap = cand; g->smem = L.total;
-                uint64_t tiles = (ix->n + tile - 1) / tile;
-                uint32_t grid = ix->opt_grid ? (uint32_t)ix->opt_grid : (uint32_t)ix->sm_count;
-                g->grid = (uint32_t)(tiles < grid ? tiles : grid);
-                if (g->grid == 0) g->grid = 1;
-                return CGVEC_OK;
+            if (L.total > kSmemBudget) continue;
+            uint32_t bytes = s * tile * g->row_words * 4;
+            if (bytes > best_bytes + best_bytes / 8) {          // keep the first (preferred) tile unless another buffers >12% more
+                best_bytes = bytes;
+                g->tile_rows = tile; g->stages = s; g->groups = groups; g->sync_interval = sync; g->cand_cap = cand; g->smem = L.total;
             }
+            break;
         }
         if (ix->opt_tile_rows) break;
     }
-    return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u (k=%u, nq=%u) does not fit the scan kernel's shared memory", ix->dim, k, nq);
+    if (!best_bytes) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u (k=%u, nq=%u) does not fit the scan kernel's shared memory", ix->dim, k, nq);
+    uint64_t tiles = (ix->n + g->tile_rows - 1) / g->tile_rows;
+    uint32_t grid = ix->opt_grid ? (uint32_t)ix->opt_grid : (uint32_t)ix->sm_count;
+    g->grid = (uint32_t)(tiles < grid ? tiles : grid);
+    if (g->grid == 0) g->grid = 1;
+    return CGVEC_OK;
 }
 
 template <typename T, int METRIC, int NQ>
@@ -303,32 +324,33 @@ int launch_scan_m(int metric, uint32_t nq, const ScanParams& p, const ScanGeom& 
 // The final level decodes into d_rows/d_scores/d_counts when given, and/or writes keys to `final_keys`.
 int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32_t lists, uint32_t k, int ascending,
                 uint64_t* final_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, cudaStream_t st,
-                size_t q_stride, size_t l_stride) {
+                size_t q_stride, size_t l_stride, uint32_t list_len = 0) {
+    if (list_len == 0) list_len = k;
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMaxKeys * 8); });
     // the kernel reads list l of query q at in + (q*n_lists + l)*k: repack when the caller's layout differs
     const uint64_t* cur = in;
     uint32_t cur_lists = lists;
     int pp = 0;
-    if (!(q_stride == (size_t)lists * k && l_stride == k)) {
-        // gathered layout [list][nq][k] -> [nq][list][k] with strided 2D copies (device to device)
+    if (!(q_stride == (size_t)lists * list_len && l_stride == list_len)) {
+        // gathered layout [list][nq][len] -> [nq][list][len] with strided 2D copies (device to device)
         uint64_t* dst = c->d_part[0];
         for (uint32_t q = 0; q < nq; ++q)
-            CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)q * lists * k, (size_t)k * 8, in + q * q_stride, l_stride * 8, (size_t)k * 8, lists,
-                                       cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)q * lists * list_len, (size_t)list_len * 8, in + q * q_stride, l_stride * 8,
+                                       (size_t)list_len * 8, lists, cudaMemcpyDeviceToDevice, st));
         cur = dst;
         pp = 1;
     }
-    const uint32_t per_cta_max = kMergeMaxKeys / k < 2 ? 2 : kMergeMaxKeys / k;
     while (true) {
+        const uint32_t per_cta_max = kMergeMaxKeys / list_len < 2 ? 2 : kMergeMaxKeys / list_len;
         uint32_t per_cta = cur_lists < per_cta_max ? cur_lists : per_cta_max;
         uint32_t n_out = (cur_lists + per_cta - 1) / per_cta;
-        uint32_t sort_n = next_pow2(per_cta * k);
+        uint32_t sort_n = next_pow2(per_cta * list_len);
         if (sort_n < 2) sort_n = 2;
         const bool last = (n_out == 1);
         uint64_t* out = last ? final_keys : c->d_part[pp];
         dim3 grid(n_out, nq);
-        merge_topk_kernel<<<grid, kMergeThreads, sort_n * 8, st>>>(cur, cur_lists, k, per_cta, sort_n, out, ascending,
+        merge_topk_kernel<<<grid, kMergeThreads, sort_n * 8, st>>>(cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
                                                                   last ? d_rows : nullptr, last ? d_scores : nullptr,
                                                                   last ? d_counts : nullptr);
         ix->launches++;
@@ -336,30 +358,59 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         if (last) break;
         cur = out;
         cur_lists = n_out;
+        list_len = k;
         pp ^= 1;
     }
     return CGVEC_OK;
 }
 
-// One exact-order scan of the local shard for `nq` (1, 2 or 4) queries already on the device at `d_q`
-// (stride = dim rounded up to 4 floats), leaving either decoded results or (world > 1) merged global keys.
-int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
-               uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+// Exchange step of a sharded index: this rank's best-k keys [nq][k] -> one NCCL all-gather -> every rank merges
+// the `world` lists and decodes.  The single collective of the path.
+int exchange_and_decode(Index* ix, SearchCtx* c, uint64_t* local_keys, uint32_t nq, uint32_t k, int ascending, cudaStream_t st,
+                        uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    size_t per_rank = (size_t)nq * k;
+    {
+        std::lock_guard<std::mutex> lk(ix->comm_mu);
+        NCCL_TRY(nccl_api().AllGather(local_keys, c->d_gather, per_rank, kNcclUint64, ix->comm, st));
+    }
+    return merge_lists(ix, c, c->d_gather, nq, ix->world, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)k, per_rank);
+}
+
+int ensure_gather(Index* ix, SearchCtx* c, uint32_t nq, uint32_t k, uint64_t** local_keys) {
+    size_t per_rank = (size_t)nq * k;
+    size_t cap_g = c->gather_cap;
+    int rc = ensure(&c->d_gather, &cap_g, per_rank * (ix->world + 1));
+    if (rc) return rc;
+    c->gather_cap = cap_g;
+    *local_keys = c->d_gather + per_rank * ix->world;
+    return CGVEC_OK;
+}
+
+int ensure_parts(SearchCtx* c, size_t need_part) {
+    if (need_part > c->part_cap) {
+        size_t cap0 = c->part_cap, cap1 = c->part_cap;
+        int rc = ensure(&c->d_part[0], &cap0, need_part); if (rc) return rc;
+        rc = ensure(&c->d_part[1], &cap1, need_part); if (rc) return rc;
+        c->part_cap = cap0 < cap1 ? cap0 : cap1;
+    }
+    return CGVEC_OK;
+}
+
+// Exact-order scan (K1) of the local shard for `nq` (1, 2 or 4) queries already on the device at `d_q`
+// (stride = dim rounded up to 4 floats).  Leaves this shard's best-k keys in `local_keys` when given, else
+// decodes straight into d_rows/d_scores/d_counts.
+int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
+                uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
     ScanGeom g;
     int rc = plan_scan(ix, k, nq, &g);
     if (rc) return rc;
     const int ascending = (metric == CGVEC_L2);
-    size_t need_part = (size_t)nq * (g.grid > (uint32_t)ix->world ? g.grid : ix->world) * k;
-    if (need_part > c->part_cap) {
-        size_t cap0 = c->part_cap, cap1 = c->part_cap;
-        rc = ensure(&c->d_part[0], &cap0, need_part); if (rc) return rc;
-        rc = ensure(&c->d_part[1], &cap1, need_part); if (rc) return rc;
-        c->part_cap = cap0 < cap1 ? cap0 : cap1;
-    }
+    rc = ensure_parts(c, (size_t)nq * (g.grid > (uint32_t)ix->world ? g.grid : ix->world) * k);
+    if (rc) return rc;
     ScanParams p = map_params(ix);
     p.rows = ix->d_rows; p.norms = ix->d_norms; p.queries = d_q; p.partials = c->d_part[0];
     p.n_rows = ix->n; p.d = ix->dim; p.ld = ix->ld; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
-    p.stages = g.stages; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
+    p.stages = g.stages; p.active_groups = g.groups; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ix->opt_timing) {
@@ -375,23 +426,222 @@ int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t 
         ix->timed.emplace_back(e0, e1);
     }
     ix->last_geom = g;
+    return merge_lists(ix, c, c->d_part[0], nq, g.grid, k, ascending, local_keys, d_rows, d_scores, d_counts, st, (size_t)g.grid * k, k);
+}
 
-    if (ix->world == 1) {
-        return merge_lists(ix, c, c->d_part[0], nq, g.grid, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)g.grid * k, k);
-    }
-    // sharded: local best-k keys -> one NCCL all-gather -> every rank merges the `world` lists
-    size_t per_rank = (size_t)nq * k;
-    size_t cap_g = c->gather_cap;
-    rc = ensure(&c->d_gather, &cap_g, per_rank * (ix->world + 1)); if (rc) return rc;
-    c->gather_cap = cap_g;
-    uint64_t* local_keys = c->d_gather + per_rank * ix->world;
-    rc = merge_lists(ix, c, c->d_part[0], nq, g.grid, k, ascending, local_keys, nullptr, nullptr, nullptr, st, (size_t)g.grid * k, k);
+int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
+               uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    if (ix->world == 1) return local_exact(ix, c, d_q, nq, k, metric, st, nullptr, d_rows, d_scores, d_counts);
+    uint64_t* local_keys = nullptr;
+    int rc = ensure_gather(ix, c, nq, k, &local_keys);
     if (rc) return rc;
-    {
-        std::lock_guard<std::mutex> lk(ix->comm_mu);
-        NCCL_TRY(nccl_api().AllGather(local_keys, c->d_gather, per_rank, kNcclUint64, ix->comm, st));
+    rc = local_exact(ix, c, d_q, nq, k, metric, st, local_keys, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    return exchange_and_decode(ix, c, local_keys, nq, k, metric == CGVEC_L2, st, d_rows, d_scores, d_counts);
+}
+
+// ---- tensor-core batched path (K2) -----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// 2-D fp16 tensor map, K (inner) x rows, 128-byte swizzle, box = 64 halves x box_rows, OOB reads as zero.
+int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstr[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)kTcKBlock, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CGVEC_OK;
+}
+
+constexpr uint32_t kTcCap = 8192;     // candidate slots per query between selects (one CTA sorts them in smem)
+
+bool tensor_path_applicable(const Index* ix, int metric, uint32_t nq) {
+    return ix->dtype == CGVEC_F16 && metric == CGVEC_COSINE && nq >= 1 && ix->n >= 1;
+}
+
+// Largest MMA N (multiple of 16) whose resident query block leaves >= 3 row stages in shared memory.
+uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
+    const uint32_t nkb = (ix->dim + kTcKBlock - 1) / kTcKBlock;
+    uint32_t limit = (uint32_t)ix->opt_tc_max_n;
+    if (limit > kTcMaxN) limit = kTcMaxN;
+    for (uint32_t N = limit & ~15u; N >= 16; N -= 16) {
+        for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s) {
+            if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { if (stages_out) *stages_out = s; return N; }
+            if (ix->opt_tc_stages) break;
+        }
     }
-    return merge_lists(ix, c, c->d_gather, nq, ix->world, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)k, per_rank);
+    return 0;
+}
+
+// Tensor-core scan of the local shard for `nq` <= N_max queries (f32, on the device, stride qstride): approximate
+// ordering on tcgen05, exact re-score of the kp survivors per query, proof of exactness; unproven queries are
+// re-run on the exact-order kernel.  Produces this shard's exact best-k keys (`local_keys` [nq][k]) or decoded results.
+int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
+                 uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCap * 8);
+    });
+    if (attr_err != cudaSuccess) return fail(CGVEC_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(attr_err));
+    uint32_t stages = 0;
+    const uint32_t n_max = tc_max_n(ix, &stages);
+    if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
+    const uint32_t N = (nq + 15) & ~15u;
+    const uint32_t nkb = (ix->dim + kTcKBlock - 1) / kTcKBlock, dpad = nkb * kTcKBlock;
+    {   // more stages when the query block is small
+        for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s)
+            if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { stages = s; break; }
+    }
+    const uint64_t n = ix->n;
+    const uint32_t want = (uint32_t)(k < n ? k : n);
+    uint32_t kp = k + (ix->opt_tc_margin > 0 ? (uint32_t)ix->opt_tc_margin : (k / 2 > 32 ? k / 2 : 32));
+    if (kp > kTcCap / 8) kp = kTcCap / 8;
+    if (kp < k) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u is too large for the tensor path", k);
+
+    int rc;
+    rc = ensure(&c->d_B, &c->B_cap, (size_t)N * dpad); if (rc) return rc;
+    rc = ensure(&c->d_tc_f, &c->tcf_cap, (size_t)3 * kTcMaxN); if (rc) return rc;
+    rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)2 * kTcMaxN + 4); if (rc) return rc;
+    rc = ensure(&c->d_cand, &c->cand_cap, (size_t)kTcMaxN * kTcCap); if (rc) return rc;
+    rc = ensure(&c->d_exact, &c->exact_cap, (size_t)kTcMaxN * (kTcCap / 8)); if (rc) return rc;
+    rc = ensure(&c->h_proven, &c->hprov_cap, (size_t)kTcMaxN + 4, true); if (rc) return rc;
+    float *d_thr = c->d_tc_f, *d_na = c->d_tc_f + kTcMaxN, *d_rho = c->d_tc_f + 2 * kTcMaxN;
+    uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTcMaxN, *d_overflow = c->d_tc_u + 2 * kTcMaxN;
+
+    tc_prep_queries_kernel<<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, c->d_B, d_na, d_rho, d_thr, d_cnt, d_overflow);
+    ix->launches++;
+    CUDA_TRY(cudaGetLastError());
+
+    CUtensorMap tmA, tmB;
+    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * 2, kTcTileRows); if (rc) return rc;
+    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * 2, N); if (rc) return rc;
+
+    TcParams p{};
+    ScanParams map = map_params(ix);
+    p.n_rows = n; p.norms = ix->d_norms; p.thr = d_thr; p.cand = c->d_cand; p.cand_count = d_cnt; p.overflow = d_overflow;
+    p.cap = kTcCap; p.nq = nq; p.N = N; p.nkb = nkb; p.stages = stages; p.metric = METRIC_COSINE;
+    p.tmem_cols = next_pow2(2 * N) < 32 ? 32 : next_pow2(2 * N);
+    p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
+    const uint32_t smem = tc_smem_layout(N, nkb, stages).total + 1024;
+
+    // geometric row ranges: after T rows the threshold sits at quantile kp/T, so the next range may hold
+    // about T*(cap/2 - kp)/kp rows before a list could reach cap/2 entries.
+    uint64_t T = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
+    while (T < n) {
+        uint64_t S = (T == 0) ? kTcCap : T * (kTcCap / 2 - kp) / kp;
+        S = (S + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+        if (S < kTcTileRows) S = kTcTileRows;
+        if (T + S > n) S = n - T;
+        p.row_begin = T; p.row_end = T + S;
+        uint64_t tiles = (S + kTcTileRows - 1) / kTcTileRows;
+        uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
+        tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+        ix->launches++;
+        CUDA_TRY(cudaGetLastError());
+        tc_select_kernel<<<nq, 256, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_thr, kTcCap, kp, kTcCap);
+        ix->launches++;
+        CUDA_TRY(cudaGetLastError());
+        T += S;
+    }
+    if (ix->opt_timing) {
+        CUDA_TRY(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(ix->ev_mu);
+        ix->timed.emplace_back(e0, e1);
+    }
+    // exact re-score of the survivors, sort, proof
+    {
+        const uint32_t total = nq * kp;
+        tc_rescore_kernel<__half><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride,
+                                                                          d_na, ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE,
+                                                                          ix->row_offset, c->d_exact);
+        ix->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    rc = ensure_parts(c, (size_t)nq * kp * 2); if (rc) return rc;
+    // sorted exact keys [nq][kp] (needed by the proof) ...
+    uint64_t* sorted = c->d_part[1];
+    rc = merge_lists(ix, c, c->d_exact, nq, 1, kp, 0, sorted, nullptr, nullptr, nullptr, st, kp, kp, kp); if (rc) return rc;
+    const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f;
+    tc_verify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c->d_cand, kTcCap, d_cnt, kp, sorted, want ? want : 1, d_na, d_rho, acc_bound, METRIC_COSINE, nq,
+                                                      d_proven, d_overflow);
+    ix->launches++;
+    CUDA_TRY(cudaGetLastError());
+    // ... and this shard's best-k (keys for the exchange, or decoded results when unsharded)
+    rc = merge_lists(ix, c, sorted, nq, 1, k, 0, local_keys, d_rows, d_scores, d_counts, st, kp, kp, kp); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_proven, d_proven, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ix->tc_batches++;
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (c->h_proven[q]) continue;
+        ix->tc_fallbacks++;                      // could not prove: this query takes the exact-order kernel
+        rc = local_exact(ix, c, d_q + (size_t)q * qstride, 1, k, CGVEC_COSINE, st, local_keys ? local_keys + (size_t)q * k : nullptr,
+                         d_rows ? d_rows + (size_t)q * k : nullptr, d_scores ? d_scores + (size_t)q * k : nullptr, d_counts ? d_counts + q : nullptr);
+        if (rc) return rc;
+    }
+    return CGVEC_OK;
+}
+
+int tensor_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
+                 uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    if (ix->world == 1) return local_tensor(ix, c, d_q, qstride, nq, k, st, nullptr, d_rows, d_scores, d_counts);
+    uint64_t* local_keys = nullptr;
+    int rc = ensure_gather(ix, c, nq, k, &local_keys);
+    if (rc) return rc;
+    rc = local_tensor(ix, c, d_q, qstride, nq, k, st, local_keys, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    return exchange_and_decode(ix, c, local_keys, nq, k, 0, st, d_rows, d_scores, d_counts);
+}
+
+// Runs nq queries (device, stride qstride) through whichever kernel family `path` selects, in batches.
+int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, int metric, int path, cudaStream_t st,
+                uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    bool tensor = false;
+    if (path == CGVEC_PATH_TENSOR) {
+        if (!tensor_path_applicable(ix, metric, nq)) return fail(CGVEC_ERR_UNSUPPORTED, "the tensor-core path serves f16 storage with the cosine metric");
+        tensor = true;
+    } else if (path == CGVEC_PATH_AUTO) {
+        tensor = tensor_path_applicable(ix, metric, nq) && nq >= (uint32_t)ix->opt_tc_min_nq && ix->n >= 4 * kTcCap && k <= kTcCap / 16;
+    }
+    uint32_t n_max = tensor ? tc_max_n(ix, nullptr) : 0;
+    if (tensor && n_max == 0) {
+        if (path == CGVEC_PATH_TENSOR) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
+        tensor = false;
+    }
+    uint32_t q0 = 0;
+    while (q0 < nq) {
+        uint32_t b;
+        int rc;
+        if (tensor) {
+            b = nq - q0 < n_max ? nq - q0 : n_max;
+            rc = tensor_batch(ix, c, d_q + (size_t)q0 * qstride, qstride, b, k, st, d_rows ? d_rows + (size_t)q0 * k : nullptr,
+                              d_scores ? d_scores + (size_t)q0 * k : nullptr, d_counts ? d_counts + q0 : nullptr);
+        } else {
+            b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
+            rc = scan_batch(ix, c, d_q + (size_t)q0 * qstride, b, k, metric, st, d_rows ? d_rows + (size_t)q0 * k : nullptr,
+                            d_scores ? d_scores + (size_t)q0 * k : nullptr, d_counts ? d_counts + q0 : nullptr);
+        }
+        if (rc) return rc;
+        q0 += b;
+    }
+    return CGVEC_OK;
 }
 
 void drain_timings(Index* ix) {
@@ -615,7 +865,6 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
     if (o.formula < CGVEC_FORMULA_SIMD || o.formula > CGVEC_FORMULA_BASELINE) return fail(CGVEC_ERR_BAD_ARG, "unknown formula %d", (int)o.formula);
     if (o.formula != CGVEC_FORMULA_SIMD && o.metric != CGVEC_COSINE)
         return fail(CGVEC_ERR_UNSUPPORTED, "formulas other than SIMD exist for cosine only (the reference has no scalar dot / L2)");
-    if (o.path == CGVEC_PATH_TENSOR) return fail(CGVEC_ERR_UNSUPPORTED, "tensor-core batched path is not built yet");
     if (o.device_io && out_ids) return fail(CGVEC_ERR_BAD_ARG, "out_ids cannot be produced with device_io");
     if (o.device_io && o.formula != CGVEC_FORMULA_SIMD) return fail(CGVEC_ERR_UNSUPPORTED, "device_io supports the SIMD formula only");
     if (nq == 0 || k == 0) {                                   // surreal_store.rs:62-64
@@ -645,14 +894,8 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
 
     if (o.device_io) {
         if (qstride != ix->dim) return finish(fail(CGVEC_ERR_UNSUPPORTED, "device_io needs dim %% 4 == 0"));
-        uint32_t q0 = 0;
-        while (q0 < nq) {
-            uint32_t b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
-            rc = scan_batch(ix, c, queries + (size_t)q0 * qstride, b, k, o.metric, st, out_rows ? out_rows + (size_t)q0 * k : nullptr,
-                            out_scores ? out_scores + (size_t)q0 * k : nullptr, out_counts ? out_counts + q0 : nullptr);
-            if (rc) return finish(rc);
-            q0 += b;
-        }
+        rc = run_queries(ix, c, queries, qstride, nq, k, o.metric, o.path, st, out_rows, out_scores, out_counts);
+        if (rc) return finish(rc);
         return finish(CGVEC_OK);
     }
 
@@ -677,14 +920,8 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         rc = ensure(&c->h_counts, &c->hcnt_cap, nq, true); if (rc) return finish(rc);
     }
     if (o.formula == CGVEC_FORMULA_SIMD) {
-        uint32_t q0 = 0;
-        while (q0 < nq) {
-            uint32_t b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
-            rc = scan_batch(ix, c, c->d_q + (size_t)q0 * qstride, b, k, o.metric, st, c->d_rows + (size_t)q0 * k, c->d_scores + (size_t)q0 * k,
-                            c->d_counts + q0);
-            if (rc) return finish(rc);
-            q0 += b;
-        }
+        rc = run_queries(ix, c, c->d_q, qstride, nq, k, o.metric, o.path, st, c->d_rows, c->d_scores, c->d_counts);
+        if (rc) return finish(rc);
         CUDA_TRY(cudaMemcpyAsync(c->h_rows, c->d_rows, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(c->h_scores, c->d_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1005,6 +1242,8 @@ CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
     out->last_scan_ms = ix->last_scan_ms;
     out->scan_ms_total = ix->scan_ms_total;
     out->scans_timed = ix->scan_timed;
+    out->tc_batches = ix->tc_batches.load();
+    out->tc_fallbacks = ix->tc_fallbacks.load();
     return CGVEC_OK;
 }
 
@@ -1019,6 +1258,10 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "timing") { ix->opt_timing = (int)value; if (!value) drain_timings(ix); }
     else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; }
     else if (k == "max_batch") ix->opt_max_nq = (int)value;
+    else if (k == "tc_min_batch") ix->opt_tc_min_nq = (int)value;
+    else if (k == "tc_stages") ix->opt_tc_stages = (int)value;
+    else if (k == "tc_max_n") ix->opt_tc_max_n = (int)value;
+    else if (k == "tc_margin") ix->opt_tc_margin = (int)value;
     else return fail(CGVEC_ERR_BAD_ARG, "unknown option '%s'", key);
     return CGVEC_OK;
 }

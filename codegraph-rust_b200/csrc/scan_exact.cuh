@@ -46,7 +46,8 @@ struct ScanParams {
     uint32_t d, ld;            // logical / padded row length in elements
     uint32_t row_words;        // shared-memory row stride in 32-bit words (>= ld*esize/4, = 8 mod 16)
     uint32_t tile_rows;        // rows per stage: 4, 8, 16 or 32
-    uint32_t stages;
+    uint32_t stages;           // multiple of active_groups (a stage is always drained by the same warp group)
+    uint32_t active_groups;    // warp groups that consume tiles, <= 8 / (tile_rows/4); the rest only help to sort
     uint32_t k;
     uint32_t cand_cap;         // power of two >= k + sync_interval*tile_rows
     uint32_t sync_interval;    // tiles between threshold syncs (multiple of the consumer group count)
@@ -181,7 +182,8 @@ __device__ __forceinline__ float sqnorm_octet(const T* __restrict__ v, uint32_t 
 
 template <typename T, int METRIC, int NQ>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_ex[];
+    uint8_t* smem = smem_ex;
     const ScanSmemLayout lay = scan_smem_layout(p.row_words, p.tile_rows, p.stages, p.d, NQ, p.cand_cap);
     uint8_t* s_rows = smem + lay.off_rows;
     float* s_norms = reinterpret_cast<float*>(smem + lay.off_norms);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t warps_per_stage = p.tile_rows >> 2;
-    const uint32_t ngroups = kScanConsumerWarps / warps_per_stage;
+    const uint32_t ngroups = p.active_groups;
     const uint32_t qstride = ((p.d * 4 + 15) & ~15u) >> 2;
     const uint32_t stage_bytes = p.tile_rows * p.row_words * 4;
     const uint32_t row_bytes = p.ld * sizeof(T);
@@ -282,7 +284,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
             }
         };
 
-        for (uint64_t n = group; n < my_tiles; n += ngroups) {
+        // Idle groups (group >= ngroups) take no tiles but still join every threshold barrier below.
+        for (uint64_t n = (group < ngroups ? group : my_tiles); n < my_tiles; n += ngroups) {
             while (next_boundary <= n) { sync_and_maybe_compact(false); next_boundary += epoch; }
             const uint32_t s = n % p.stages;
             mbar_wait(&full_bar[s], (n / p.stages) & 1);

@@ -1,0 +1,369 @@
+// scan_tc.cuh — K2: batched-query scan on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), fp16 rows.
+//
+// The reference has no batched kernel: its "batch" shapes are a per-query loop
+// (batch_cosine_similarity_avx2, crates/codegraph-vector/src/simd_ops.rs:85-99) and concurrent
+// search_similar calls (multi_vector_search, src/search.rs:347-361).  For nq >= ~8 queries the scan is a
+// genuine dense contraction S[row, q] = sum_k R[row,k] * Q[q,k], so it goes to tcgen05.mma.
+//
+// Shape.  One persistent CTA per SM.  The query block B (N = nq padded to 16, K = d padded to 64) is TMA-loaded
+// ONCE and stays resident in shared memory as SWIZZLE_128B K-major tiles; the row stream A (128 rows x 64
+// halves = 16 KB per stage) flows through a ring of TMA stages.  Warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane issues 4 x tcgen05.mma.cta_group::1.kind::f16 M=128,N,K=16 per stage, then
+// tcgen05.commit frees the stage), warp 2 owns the TMEM allocation, warps 4-7 are the epilogue: they pull
+// the 128 x N fp32 accumulator tile out of TMEM (tcgen05.ld 32x32b), scale by 1/|row|, compare against the
+// per-query threshold and append the rare survivors (key = ord(score) << 32 | ~row) to per-query candidate
+// lists in global memory with warp-aggregated atomics.  Two TMEM accumulator buffers let the epilogue of
+// tile t overlap the MMAs of tile t+1.  The Q x N score matrix is never written.
+//
+// Exactness.  Tensor-core scores are only an ORDERING HEURISTIC here (fp16 x fp16 products are exact in fp32,
+// accumulation order differs from the oracle, queries are rounded to fp16).  The host side (cgvec_api.cu,
+// search_tensor) scans the shard in a few geometrically growing row ranges, tightening each query's
+// threshold to its current kp-th best between ranges (tc_select_kernel), then re-scores the kp survivors per
+// query in the reference's exact order (K4), re-ranks, and PROVES with a rigorous error bound that no
+// discarded row can reach the top-k; an unproven query is re-run on the exact-order kernel (scan_exact.cuh).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "scan_exact.cuh"
+
+namespace cgv {
+
+constexpr int kTcThreads = 256;
+constexpr int kTcTileRows = 128;
+constexpr int kTcKBlock = 64;                 // halves per 128-byte swizzle row
+constexpr int kTcStageBytes = kTcTileRows * 128;
+constexpr int kTcMaxN = 128;
+
+struct TcParams {
+    uint64_t n_rows;            // local rows of the shard (rows >= n_rows are TMA zero fill and masked)
+    uint64_t row_begin, row_end;   // this launch scans local rows [row_begin, row_end); row_begin % 128 == 0
+    const float* norms;         // squared row norms (reference order); cosine only
+    const float* thr;           // [N] per-query thresholds in dot/|row| units
+    uint64_t* cand;             // [N][cap] candidate keys
+    uint32_t* cand_count;       // [N]
+    uint32_t* overflow;         // set when a list would exceed cap
+    uint32_t cap;
+    uint32_t nq;                // real queries (<= N)
+    uint32_t N;                 // MMA N: nq rounded up to 16
+    uint32_t nkb;               // ceil(d / 64)
+    uint32_t stages;
+    uint32_t metric;            // METRIC_COSINE or METRIC_DOT
+    uint32_t tmem_cols;         // power of two >= 2*N, >= 32
+    uint64_t row_offset;
+    uint32_t blk_rows, n_shards, shard_id;
+};
+
+struct TcSmemLayout { uint32_t off_b, off_a, off_bars, off_misc, total; };
+__host__ __device__ inline TcSmemLayout tc_smem_layout(uint32_t N, uint32_t nkb, uint32_t stages) {
+    TcSmemLayout L;
+    L.off_b = 0;
+    L.off_a = nkb * N * 128;                                   // multiple of 1024 because N % 8 == 0
+    L.off_bars = L.off_a + stages * kTcStageBytes;
+    L.off_misc = L.off_bars + (2 * stages + 1 + 4) * 8;
+    L.total = L.off_misc + 16;
+    return L;
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
+// LBO>>4 [16,30) (ignored for swizzled K-major, 1), SBO>>4 [32,46) = 1024 B between 8-row groups, version 1
+// [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ inline uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- the kernel -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment in the shared window; the launch reserves 1 KB of slack for this
+    uint8_t* smem = smem_tc_raw + ((1024u - (smem_u32(smem_tc_raw) & 1023u)) & 1023u);
+    const TcSmemLayout lay = tc_smem_layout(p.N, p.nkb, p.stages);
+    uint8_t* sB = smem + lay.off_b;
+    uint8_t* sA = smem + lay.off_a;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* b_bar = empty_bar + p.stages;
+    uint64_t* tfull_bar = b_bar + 1;          // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;     // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + lay.off_misc);
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t first_tile = p.row_begin / kTcTileRows;
+    const uint64_t num_tiles = (p.row_end - p.row_begin + kTcTileRows - 1) / kTcTileRows;
+    const uint64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(b_bar, 1);
+        mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+        mbar_init(&tempty_bar[0], 4); mbar_init(&tempty_bar[1], 4);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(s_tmem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            const uint64_t pol = l2_policy_evict_first();
+            mbar_arrive_expect_tx(b_bar, p.nkb * p.N * 128);
+            for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.N * 128, &tmB, kb * kTcKBlock, 0, b_bar);
+            uint64_t it = 0;
+            for (uint64_t t = 0; t < my_tiles; ++t) {
+                const int row0 = (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows);
+                for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
+                    const uint32_t s = it % p.stages;
+                    if (it >= p.stages) mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
+                    mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
+                    tma_load_2d_hint(sA + (size_t)s * kTcStageBytes, &tmA, kb * kTcKBlock, row0, &full_bar[s], pol);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(kTcTileRows, p.N);
+            mbar_wait(b_bar, 0);
+            tc_fence_after();
+            uint64_t it = 0;
+            for (uint64_t t = 0; t < my_tiles; ++t) {
+                const uint32_t buf = t & 1;
+                mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * p.N;
+                for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
+                    const uint32_t s = it % p.stages;
+                    mbar_wait(&full_bar[s], (it / p.stages) & 1);        // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kTcStageBytes);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)kb * p.N * 128);
+#pragma unroll
+                    for (uint32_t k = 0; k < kTcKBlock / 16; ++k)
+                        umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);                          // stage free once these MMAs retire
+                }
+                umma_commit(&tfull_bar[buf]);                            // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
+        const uint32_t q4 = warp & 3;                                    // TMEM lane quarter this warp may access
+        for (uint64_t t = 0; t < my_tiles; ++t) {
+            const uint32_t buf = t & 1;
+            const uint64_t row = (first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows + q4 * 32 + lane;   // local row
+            const bool valid = row < p.n_rows && row < p.row_end;
+            float inv = 1.0f;
+            if (p.metric == METRIC_COSINE) {
+                const float nb = valid ? p.norms[row] : 0.0f;
+                inv = nb > 0.0f ? rsqrtf(nb) : 0.0f;                     // zero-norm row -> cosine 0 (simd_ops.rs:73-74)
+            }
+            mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * p.N + ((q4 * 32u) << 16);
+            for (uint32_t c0 = 0; c0 < p.N; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld_x16(taddr + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) {
+                    const uint32_t q = c0 + j;
+                    const float v = __uint_as_float(r[j]) * inv;
+                    const bool pass = valid && q < p.nq && v >= __ldg(&p.thr[q]);
+                    const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                    if (mask) {                                          // warp-uniform, rare in steady state
+                        uint32_t base = 0;
+                        const int leader = __ffs(mask) - 1;
+                        if ((int)lane == leader) base = atomicAdd(&p.cand_count[q], (uint32_t)__popc(mask));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (pass) {
+                            const uint32_t pos = base + __popc(mask & ((1u << lane) - 1));
+                            if (pos < p.cap) {
+                                const uint64_t b = row / p.blk_rows, rr = row - b * p.blk_rows;
+                                const uint32_t g = (uint32_t)((b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);
+                                p.cand[(size_t)q * p.cap + pos] = make_key(v, g, false);
+                            } else {
+                                *p.overflow = 1u;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---- between row ranges: keep each query's best kp candidates, publish the new threshold ---------------------
+// grid = nq, block = 256, dynamic smem = sort_cap * 8.  cand[q][0..count) -> sorted best kp in cand[q][0..kp).
+__global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count,
+                                                         float* __restrict__ thr, uint32_t cap, uint32_t kp, uint32_t sort_cap) {
+    extern __shared__ __align__(16) uint64_t s_sel_keys[];
+    uint64_t* s_keys = s_sel_keys;
+    const uint32_t q = blockIdx.x;
+    uint32_t cnt = cand_count[q];
+    if (cnt > cap) cnt = cap;
+    uint32_t n = 2;
+    while (n < cnt) n <<= 1;
+    if (n > sort_cap) n = sort_cap;
+    uint64_t* c = cand + (size_t)q * cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = (i < cnt) ? c[i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_keys, n, threadIdx.x, blockDim.x, 0);
+    const uint32_t keep = cnt < kp ? cnt : kp;
+    for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) c[i] = (i < keep) ? s_keys[i] : 0ull;
+    if (threadIdx.x == 0) {
+        cand_count[q] = keep;
+        thr[q] = (keep >= kp) ? key_score(s_keys[kp - 1], false) : __int_as_float(0xff800000);   // -inf until kp found
+    }
+}
+
+// ---- query preparation: f32 queries -> fp16 B operand (zero padded), exact |q|^2, rounding-error ratio -------
+// One octet per query.  rho[q] >= ||q - fp16(q)|| / ||q||  (inflated 1%) feeds the host-side error bound.
+__global__ void tc_prep_queries_kernel(const float* __restrict__ q, uint32_t qstride, uint32_t nq, uint32_t N, uint32_t d, uint32_t dpad,
+                                       __half* __restrict__ B, float* __restrict__ na, float* __restrict__ rho, float* __restrict__ thr,
+                                       uint32_t* __restrict__ cand_count, uint32_t* __restrict__ overflow) {
+    const uint32_t octet = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int L = threadIdx.x & 7;
+    const uint32_t qi = octet < N ? octet : N - 1;
+    const bool real = octet < nq;
+    const float* v = q + (size_t)(qi < nq ? qi : 0) * qstride;
+    float nsq = sqnorm_octet(v, d, L);                     // reference order (adaptive) -> exact na
+    float e2 = 0.0f, s2 = 0.0f;
+    for (uint32_t i = L; i < dpad; i += 8) {
+        float x = (real && i < d) ? v[i] : 0.0f;
+        __half h = __float2half_rn(x);
+        if (octet < N) B[(size_t)qi * dpad + i] = h;
+        float e = x - __half2float(h);
+        e2 += e * e;
+        s2 += x * x;
+    }
+    for (int o = 4; o; o >>= 1) { e2 += __shfl_xor_sync(0xffffffffu, e2, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (L == 0 && octet < N) {
+        na[qi] = real ? nsq : 0.0f;
+        rho[qi] = (real && s2 > 0.0f) ? 1.01f * sqrtf(e2 / s2) + 1e-7f : 0.0f;
+        thr[qi] = __int_as_float(0xff800000);
+        cand_count[qi] = 0;
+    }
+    if (octet == 0 && L == 0) *overflow = 0;
+}
+
+// ---- exact re-scoring of the survivors (K4, batched): keys_in[q][i] (approx) -> keys_out[q][i] (exact SIMD-order score) ----
+template <typename T>
+__global__ void tc_rescore_kernel(const T* __restrict__ rows, uint32_t d, uint32_t ld, const float* __restrict__ q, uint32_t qstride,
+                                  const float* __restrict__ na, const float* __restrict__ norms, const uint64_t* __restrict__ keys_in,
+                                  uint32_t cap, uint32_t kp, uint32_t nq, int metric, uint64_t row_offset,
+                                  uint64_t* __restrict__ keys_out) {
+    const uint32_t octet = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int L = threadIdx.x & 7;
+    const uint32_t total = nq * kp;
+    const uint32_t pi = octet < total ? octet : total - 1;
+    const uint32_t qi = pi / kp, ci = pi - qi * kp;
+    const uint64_t key = keys_in[(size_t)qi * cap + ci];
+    const bool present = key != 0ull;
+    const uint32_t grow = key_row(key);
+    const uint64_t lrow = present ? (uint64_t)grow - row_offset : 0;
+    const T* row = rows + lrow * ld;
+    const float* qv = q + (size_t)qi * qstride;
+    float res = 0.0f;
+    const float naq = na[qi];
+    const float nb = (metric == METRIC_COSINE) ? norms[lrow] : 0.0f;
+    if (metric == METRIC_COSINE) score_row_octet<T, METRIC_COSINE, 1>(row, qv, 0, d, L, &naq, nb, &res);
+    else score_row_octet<T, METRIC_DOT, 1>(row, qv, 0, d, L, &naq, nb, &res);
+    if (L == 0 && octet < total) keys_out[(size_t)qi * kp + ci] = present ? make_key(res, grow, false) : 0ull;
+}
+
+// ---- proof obligation per query: exact k-th score must beat (weakest kept approximate score + eps) ----------------
+// approx list: cand[q][0..kp) sorted by approximate value v = dot/|row| (cosine) ; exact list: sorted exact keys.
+// proven[q] = 1 when fewer than kp rows survived in total (nothing was discarded by rank) or
+//             exact_k > v_kp / |q| + eps_q   with eps_q = rho_q + acc_bound(d).
+__global__ void tc_verify_kernel(const uint64_t* __restrict__ approx, uint32_t cap, const uint32_t* __restrict__ counts, uint32_t kp,
+                                 const uint64_t* __restrict__ exact_sorted, uint32_t k, const float* __restrict__ na,
+                                 const float* __restrict__ rho, float acc_bound, int metric, uint32_t nq, uint32_t* __restrict__ proven,
+                                 const uint32_t* __restrict__ overflow) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t ok = 0;
+    if (*overflow == 0) {
+        if (counts[q] < kp) ok = 1;
+        else {
+            const float v_kp = key_score(approx[(size_t)q * cap + kp - 1], false);
+            const uint64_t ek = exact_sorted[(size_t)q * kp + (k < kp ? k : kp) - 1];
+            const float s_k = key_score(ek, false);
+            if (metric == METRIC_COSINE) {
+                const float nq_ = sqrtf(na[q]);
+                if (nq_ > 0.0f && ek != 0ull && s_k == s_k) {
+                    const float a = v_kp / nq_;
+                    ok = (s_k > a + (rho[q] + acc_bound) * 1.0001f) ? 1u : 0u;
+                }                                                // zero / NaN queries stay unproven -> exact-order fallback
+            }
+        }
+    }
+    proven[q] = ok;
+}
+
+}  // namespace cgv

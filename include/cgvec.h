@@ -173,6 +173,8 @@ typedef struct {
     float last_scan_ms;          /* device time of the last scan kernel when option "timing" is on      */
     double scan_ms_total;        /* sum / count of scan-kernel device times since "reset_timing"         */
     uint64_t scans_timed;
+    uint64_t tc_batches;         /* query batches served by the tensor-core path                         */
+    uint64_t tc_fallbacks;       /* queries it could not prove exact and re-ran on the exact-order kernel */
 } cgvec_stats;
 int cgvec_get_stats(const cgvec_index* idx, cgvec_stats* out);
 int cgvec_set_option(cgvec_index* idx, const char* key, int64_t value);   /* tuning knobs, see DESIGN.md */

@@ -316,3 +316,41 @@ def test_config2_full_size_1m_x_768(cg, oracle):
     st = ix.stats()
     assert st.grid == st.sm_count
     ix.close()
+
+
+@pytest.mark.parametrize("d", [384, 1024, 1536, 2048, 4096])
+def test_deep_pipeline_every_reference_dimension(cg, oracle, d):
+    """The SurrealDB path whitelists these dims (surrealdb_storage.rs:1933-1954).  Enough rows that every CTA
+    wraps its stage ring several times (mbarrier phases flip) whatever stage count the planner picks."""
+    rng = np.random.default_rng(d)
+    n = 148 * 16 * 10 + 7
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal(d).astype(np.float32)
+    _check_exact(cg, oracle, rows, q, 10, "cosine")
+
+
+@pytest.mark.parametrize("tile,stages", [(4, 8), (8, 4), (8, 8), (16, 2), (16, 4), (16, 6), (32, 2), (32, 3)])
+def test_every_launch_geometry_is_exact(cg, oracle, tile, stages):
+    rng = np.random.default_rng(tile * 10 + stages)
+    n, d = 148 * 32 * 9 + 3, 256
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    qs = rng.standard_normal((2, d)).astype(np.float32)
+    ix = cg.Index(d)
+    ix.add(rows)
+    ix.set_option("tile_rows", tile); ix.set_option("stages", stages)
+    for hint in (0, 1):
+        ix.set_option("l2_hint", hint)
+        r, s, c = ix.search(qs, 33)
+        st = ix.stats()
+        assert st.tile_rows == tile and st.stages == stages
+        for qi in range(2):
+            wi, ws = oracle.parallel_top_k_search(qs[qi], rows, 33)
+            assert r[qi].tolist() == wi.tolist() and s[qi].tobytes() == ws.tobytes()
+    # a stage count that no full grouping divides still runs exactly (fewer active warp groups)
+    for tile, stages in ((8, 7), (8, 3), (16, 3), (16, 5), (4, 6)):
+        ix.set_option("tile_rows", tile); ix.set_option("stages", stages)
+        r, s, c = ix.search(qs[0], 5)
+        assert ix.stats().stages == stages
+        wi, ws = oracle.parallel_top_k_search(qs[0], rows, 5)
+        assert r[0].tolist() == wi.tolist() and s[0].tobytes() == ws.tobytes()
+    ix.close()

@@ -1,0 +1,91 @@
+"""K2 (tcgen05 batched path) parity: same bar as the exact path — indices bit-exact, scores bit-identical to the
+oracle (rows widened f16 -> f32) — plus evidence that the tensor cores really carried the load (no silent
+exact-kernel fallback on well-separated data)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cg, oracle, n, d, nq, k, seed, expect_no_fallback=True, rows=None, queries=None):
+    rng = np.random.default_rng(seed)
+    if rows is None:
+        rows = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    if queries is None:
+        queries = rng.standard_normal((nq, d)).astype(np.float32)
+    ref_rows = rows.astype(np.float16).astype(np.float32)
+    ix = cg.Index(d, cg.F16)
+    try:
+        ix.add(rows)
+        r, s, c = ix.search(queries, k, cg.COSINE, path=cg.PATH_TENSOR)
+        st = ix.stats()
+        assert st.tc_batches >= 1
+        for qi in range(queries.shape[0]):
+            wi, ws = oracle.parallel_top_k_search(queries[qi], ref_rows, k)
+            assert int(c[qi]) == len(wi)
+            assert r[qi, :len(wi)].tolist() == wi.tolist(), (qi, r[qi, :len(wi)][:8], wi[:8])
+            assert np.array_equal(s[qi, :len(wi)], ws), (qi,)
+        if expect_no_fallback:
+            assert st.tc_fallbacks == 0, f"{st.tc_fallbacks} queries fell back to the exact kernel"
+        return st
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("d", [64, 128, 768, 1024])
+def test_tensor_path_matches_oracle(cg, oracle, d):
+    _run(cg, oracle, 60_000, d, 64, 10, seed=d)
+
+
+def test_tensor_path_k100_config4_shape(cg, oracle):
+    """BASELINE config 4's per-GPU shape at reduced N: d=1024 f16, batch-64, top-100."""
+    _run(cg, oracle, 120_000, 1024, 64, 100, seed=4)
+
+
+@pytest.mark.parametrize("nq", [1, 15, 16, 17, 100, 130])
+def test_tensor_path_batch_padding_and_splitting(cg, oracle, nq):
+    _run(cg, oracle, 40_000, 256, nq, 10, seed=nq)
+
+
+@pytest.mark.parametrize("d", [40, 100, 1000])
+def test_tensor_path_ragged_dimensions(cg, oracle, d):
+    """d % 64 != 0: the TMA boxes read zeros past the row end; d % 8 != 0 exercises the exact re-score's scalar tail."""
+    _run(cg, oracle, 30_000, d, 32, 10, seed=d)
+
+
+def test_tensor_path_small_index_and_row_tail(cg, oracle):
+    _run(cg, oracle, 8_192 + 77, 128, 16, 10, seed=1)
+    _run(cg, oracle, 300, 128, 16, 10, seed=2)
+    _run(cg, oracle, 5, 128, 16, 10, seed=3)
+
+
+def test_tensor_path_duplicates_fall_back_but_stay_exact(cg, oracle):
+    """Massive exact ties defeat the separation proof (and overflow the candidate lists): those queries must be
+    re-run on the exact-order kernel and still return the lowest row indices among equals."""
+    rng = np.random.default_rng(7)
+    base = (rng.standard_normal((3, 128)) / 11).astype(np.float32)
+    rows = np.repeat(base, 20_000, axis=0)[rng.permutation(60_000)]
+    qs = np.concatenate([base[:1], rng.standard_normal((15, 128)).astype(np.float32)])
+    st = _run(cg, oracle, 0, 128, 0, 20, seed=0, expect_no_fallback=False, rows=rows, queries=qs)
+    assert st.tc_fallbacks >= 1
+
+
+def test_auto_path_picks_tensor_for_large_f16_batches(cg, oracle):
+    rng = np.random.default_rng(9)
+    rows = (rng.standard_normal((50_000, 128)) / 11).astype(np.float32)
+    qs = rng.standard_normal((32, 128)).astype(np.float32)
+    ix = cg.Index(128, cg.F16)
+    ix.add(rows)
+    r, s, c = ix.search(qs, 10)                       # PATH_AUTO
+    assert ix.stats().tc_batches >= 1
+    r1, s1, c1 = ix.search(qs[:2], 10)                # small batch -> exact kernel
+    assert ix.stats().tc_batches == 1
+    assert r1.tolist() == r[:2].tolist() and s1.tobytes() == s[:2].tobytes()
+    ix.close()
+    # f32 storage never takes the f16 tensor path
+    ix = cg.Index(128, cg.F32)
+    ix.add(rows)
+    with pytest.raises(cg.CgvecError) as e:
+        ix.search(qs, 10, path=cg.PATH_TENSOR)
+    assert e.value.code == cg.ERR_UNSUPPORTED
+    ix.close()
