@@ -142,11 +142,14 @@ def version() -> str:
 # -------------------------------------------------------------------------------------------------
 class Index:
     def __init__(self, dim: int, dtype: int = F32, device: int = 0, rank: int = 0, world: int = 1,
-                 nccl_unique_id: Optional[bytes] = None, row_offset: int = 0):
+                 nccl_unique_id: Optional[bytes] = None, row_offset: int = 0, devices: Optional[Sequence[int]] = None):
         L = load_library()
         self._h = C.c_void_p()
         self.dim, self.dtype, self.device, self.rank, self.world, self.row_offset = dim, dtype, device, rank, world, row_offset
-        if world == 1 and rank == 0 and row_offset == 0:
+        if devices is not None and len(devices) > 1:          # single-process multi-GPU index
+            dev = (C.c_int * len(devices))(*devices)
+            _check(L.cgvec_create(dim, dtype, dev, len(devices), C.byref(self._h)))
+        elif world == 1 and rank == 0 and row_offset == 0:
             dev = (C.c_int * 1)(device)
             _check(L.cgvec_create(dim, dtype, dev, 1, C.byref(self._h)))
         else:

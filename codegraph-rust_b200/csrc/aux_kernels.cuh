@@ -155,30 +155,55 @@ __global__ void make_keys_kernel(const float* __restrict__ scores, const uint64_
 // out : [nq][n_out][k]   where CTA (x, y) merges lists [x*lists_per_cta, ...) of query y and keeps the best k.
 // When out_rows/out_scores/out_counts are given (final level, n_out == 1) the winners are decoded too.
 constexpr int kMergeThreads = 256;
+constexpr uint32_t kTournamentMaxK = 128;
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_t* __restrict__ in, uint32_t n_lists,
                                                                     uint32_t list_len, uint32_t k, uint32_t lists_per_cta,
                                                                     uint32_t sort_n, uint64_t* __restrict__ out, int ascending,
                                                                     uint64_t* __restrict__ out_rows,
                                                                     float* __restrict__ out_scores,
-                                                                    uint32_t* __restrict__ out_counts) {
+                                                                    uint32_t* __restrict__ out_counts, int sorted_in) {
     extern __shared__ __align__(16) uint64_t s_merge_keys[];
     uint64_t* s_keys = s_merge_keys;
+    // Let a programmatically-dependent successor (the next query's scan, which does not read our output) start now.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t q = blockIdx.y, n_out = gridDim.x;
     const uint32_t first = blockIdx.x * lists_per_cta;
     const uint32_t lists = min(lists_per_cta, n_lists - first);
     const uint64_t* src = in + ((size_t)q * n_lists + first) * list_len;
     const uint32_t total = lists * list_len;
-    for (uint32_t i = threadIdx.x; i < sort_n; i += kMergeThreads) s_keys[i] = (i < total) ? src[i] : 0ull;
-    __syncthreads();
-    bitonic_sort_desc(s_keys, sort_n, threadIdx.x, kMergeThreads, 0);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t* best;                                       // the CTA's best-k keys, descending, 0-padded
+    if (sorted_in && k <= kTournamentMaxK && lists <= 32 * (kMergeThreads / 32)) {
+        // tournament: every warp reduces up to 32 sorted lists to one, then warp 0 reduces the <= 8 survivors
+        uint64_t* lvl = s_keys + sort_n;                        // [8][k] after the staged lists
+        for (uint32_t i = threadIdx.x; i < total; i += kMergeThreads) s_keys[i] = src[i];
+        __syncthreads();
+        const uint32_t nw = (lists + 31) / 32;
+        if (warp < nw)
+            warp_tournament_topk(s_keys + (size_t)warp * 32 * list_len, min(32u, lists - warp * 32), list_len, list_len, k, lvl + (size_t)warp * k, lane);
+        __syncthreads();
+        if (nw > 1) {
+            if (warp == 0) warp_tournament_topk(lvl, nw, k, k, k, s_keys, lane);
+            __syncthreads();
+            best = s_keys;
+        } else {
+            best = lvl;
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < sort_n; i += kMergeThreads) s_keys[i] = (i < total) ? src[i] : 0ull;
+        __syncthreads();
+        bitonic_sort_desc(s_keys, sort_n, threadIdx.x, kMergeThreads, 0);
+        best = s_keys;
+    }
+    const uint32_t avail = (sorted_in && k <= kTournamentMaxK && lists <= 32 * (kMergeThreads / 32)) ? k : sort_n;
     if (out) {
         uint64_t* dst = out + ((size_t)q * n_out + blockIdx.x) * k;
-        for (uint32_t i = threadIdx.x; i < k; i += kMergeThreads) dst[i] = (i < sort_n) ? s_keys[i] : 0ull;
+        for (uint32_t i = threadIdx.x; i < k; i += kMergeThreads) dst[i] = (i < avail) ? best[i] : 0ull;
     }
     if (out_rows || out_scores || out_counts) {
         uint32_t cnt = 0;
         for (uint32_t i = threadIdx.x; i < k; i += kMergeThreads) {
-            const uint64_t key = (i < sort_n) ? s_keys[i] : 0ull;
+            const uint64_t key = (i < avail) ? best[i] : 0ull;
             const bool valid = key != 0ull;
             if (out_rows) out_rows[(size_t)q * k + i] = valid ? (uint64_t)key_row(key) : ~0ull;
             if (out_scores) out_scores[(size_t)q * k + i] = valid ? key_score(key, ascending != 0) : 0.0f;

@@ -17,6 +17,7 @@
 #include "../../include/cgvec.h"
 #include "aux_kernels.cuh"
 #include "common.cuh"
+#include "exchange.cuh"
 #include "nccl_dyn.h"
 #include "scan_exact.cuh"
 #include "scan_tc.cuh"
@@ -87,7 +88,8 @@ struct SearchCtx {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     float* d_q = nullptr;        size_t q_cap = 0;       // floats
-    uint64_t* d_part[2] = {nullptr, nullptr}; size_t part_cap = 0;   // keys
+    uint64_t* d_part[2] = {nullptr, nullptr}; size_t part_cap = 0;   // keys (merge ping-pong)
+    uint64_t* d_scan[2] = {nullptr, nullptr}; size_t scan_cap = 0; uint32_t scan_flip = 0;   // per-CTA partials, double buffered (PDL)
     uint64_t* d_gather = nullptr; size_t gather_cap = 0;  // keys
     uint64_t* d_rows = nullptr;  float* d_scores = nullptr; uint32_t* d_counts = nullptr; size_t out_cap = 0, cnt_cap = 0;
     uint64_t* d_tmp_rows = nullptr; float* d_tmp_scores = nullptr; size_t tmp_cap = 0;
@@ -103,7 +105,7 @@ struct SearchCtx {
 };
 
 struct ScanGeom {
-    uint32_t tile_rows, stages, groups, sync_interval, cand_cap, row_words, grid, smem;
+    uint32_t tile_rows, stages, groups, sync_interval, cand_cap, row_words, grid, smem, pdl;
 };
 
 struct Index {
@@ -112,6 +114,8 @@ struct Index {
     int device = 0;
     int rank = 0, world = 1;
     uint64_t row_offset = 0;
+    uint32_t blk_rows = 1u << 30, n_shards = 1, shard_id = 0;   // global row = ((local/blk)*n_shards + shard_id)*blk + local%blk + row_offset
+    std::vector<Index*> parts;    // non-empty on the parent of a single-process multi-device index (one shard per device)
     int sm_count = 0;
 
     void* d_rows = nullptr;
@@ -124,6 +128,12 @@ struct Index {
 
     nccl_comm_t comm = nullptr;
     std::mutex comm_mu;           // collectives must be issued in the same order on every rank
+    // peer-memory exchange (exchange.cuh): own buffer + every rank's buffer mapped through CUDA IPC
+    uint8_t* xbuf = nullptr;
+    uint8_t* xpeer[kXchgMaxWorld] = {nullptr};
+    bool p2p = false;
+    uint32_t xseq = 0;
+    int opt_p2p = 1;
 
     std::mutex pool_mu;
     std::vector<SearchCtx*> pool;
@@ -131,6 +141,8 @@ struct Index {
 
     // knobs (cgvec_set_option)
     int opt_tile_rows = 0, opt_stages = 0, opt_sync = 0, opt_l2_hint = 0, opt_grid = 0, opt_timing = 0, opt_max_nq = kScanMaxQ;
+    int opt_pdl = 1;
+    int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 16;
     int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0;
     std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
 
@@ -189,7 +201,7 @@ void ctx_release(Index* ix, SearchCtx* c) {
     ix->pool.push_back(c);
 }
 void ctx_free(SearchCtx* c) {
-    cudaFree(c->d_q); cudaFree(c->d_part[0]); cudaFree(c->d_part[1]); cudaFree(c->d_gather);
+    cudaFree(c->d_q); cudaFree(c->d_part[0]); cudaFree(c->d_part[1]); cudaFree(c->d_scan[0]); cudaFree(c->d_scan[1]); cudaFree(c->d_gather);
     cudaFree(c->d_rows); cudaFree(c->d_scores); cudaFree(c->d_counts); cudaFree(c->d_tmp_rows); cudaFree(c->d_tmp_scores);
     cudaFree(c->d_B); cudaFree(c->d_tc_f); cudaFree(c->d_tc_u); cudaFree(c->d_cand); cudaFree(c->d_exact); cudaFreeHost(c->h_proven);
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_rows); cudaFreeHost(c->h_scores); cudaFreeHost(c->h_counts);
@@ -231,9 +243,9 @@ int grow(Index* ix, uint64_t need, bool exact = false) {
 ScanParams map_params(const Index* ix) {
     ScanParams p{};
     p.row_offset = ix->row_offset;
-    p.blk_rows = 1u << 30;
-    p.n_shards = 1;
-    p.shard_id = 0;
+    p.blk_rows = ix->blk_rows;
+    p.n_shards = ix->n_shards;
+    p.shard_id = ix->shard_id;
     return p;
 }
 
@@ -289,16 +301,39 @@ int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
     return CGVEC_OK;
 }
 
+// cudaFuncSetAttribute is per device: remember which (function, device) pairs have been raised already.
+template <typename F>
+int ensure_smem_attr(F func, uint32_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* key = reinterpret_cast<const void*>(func);
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& d : done) if (d.first == key && d.second == dev) return CGVEC_OK;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(CGVEC_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+    done.emplace_back(key, dev);
+    return CGVEC_OK;
+}
+
 template <typename T, int METRIC, int NQ>
 int launch_scan_t(const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(scan_exact_kernel<T, METRIC, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    });
-    if (attr_err != cudaSuccess) return fail(CGVEC_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(attr_err));
-    scan_exact_kernel<T, METRIC, NQ><<<g.grid, kScanThreads, g.smem, st>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    int arc = ensure_smem_attr(scan_exact_kernel<T, METRIC, NQ>, kSmemBudget);
+    if (arc) return arc;
+    // Programmatic dependent launch: the kernel ahead of us in the stream is normally the previous query's merge,
+    // whose output we do not read (partials are double buffered), so our CTAs may start as soon as it has started.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g.grid);
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, scan_exact_kernel<T, METRIC, NQ>, p));
     return CGVEC_OK;
 }
 template <typename T, int METRIC>
@@ -324,10 +359,12 @@ int launch_scan_m(int metric, uint32_t nq, const ScanParams& p, const ScanGeom& 
 // The final level decodes into d_rows/d_scores/d_counts when given, and/or writes keys to `final_keys`.
 int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32_t lists, uint32_t k, int ascending,
                 uint64_t* final_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, cudaStream_t st,
-                size_t q_stride, size_t l_stride, uint32_t list_len = 0) {
+                size_t q_stride, size_t l_stride, uint32_t list_len = 0, int sorted_in = 1) {
     if (list_len == 0) list_len = k;
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMaxKeys * 8); });
+    {
+        int arc = ensure_smem_attr(merge_topk_kernel, kMergeMaxKeys * 8);
+        if (arc) return arc;
+    }
     // the kernel reads list l of query q at in + (q*n_lists + l)*k: repack when the caller's layout differs
     const uint64_t* cur = in;
     uint32_t cur_lists = lists;
@@ -342,7 +379,8 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         pp = 1;
     }
     while (true) {
-        const uint32_t per_cta_max = kMergeMaxKeys / list_len < 2 ? 2 : kMergeMaxKeys / list_len;
+        uint32_t per_cta_max = (kMergeMaxKeys - 8 * kTournamentMaxK) / list_len < 2 ? 2 : (kMergeMaxKeys - 8 * kTournamentMaxK) / list_len;
+        if (per_cta_max > 256) per_cta_max = 256;
         uint32_t per_cta = cur_lists < per_cta_max ? cur_lists : per_cta_max;
         uint32_t n_out = (cur_lists + per_cta - 1) / per_cta;
         uint32_t sort_n = next_pow2(per_cta * list_len);
@@ -350,15 +388,19 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         const bool last = (n_out == 1);
         uint64_t* out = last ? final_keys : c->d_part[pp];
         dim3 grid(n_out, nq);
-        merge_topk_kernel<<<grid, kMergeThreads, sort_n * 8, st>>>(cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
-                                                                  last ? d_rows : nullptr, last ? d_scores : nullptr,
-                                                                  last ? d_counts : nullptr);
+        const bool tournament = sorted_in && k <= kTournamentMaxK && per_cta <= 256;
+        const size_t smem = tournament ? ((size_t)per_cta * list_len + 8 * k) * 8 : (size_t)sort_n * 8;
+        if (tournament) sort_n = per_cta * list_len;            // staging area size (keys) ahead of the level-2 lists
+        merge_topk_kernel<<<grid, kMergeThreads, smem, st>>>(cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
+                                                            last ? d_rows : nullptr, last ? d_scores : nullptr,
+                                                            last ? d_counts : nullptr, sorted_in);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
         if (last) break;
         cur = out;
         cur_lists = n_out;
         list_len = k;
+        sorted_in = 1;
         pp ^= 1;
     }
     return CGVEC_OK;
@@ -400,15 +442,28 @@ int ensure_parts(SearchCtx* c, size_t need_part) {
 // (stride = dim rounded up to 4 floats).  Leaves this shard's best-k keys in `local_keys` when given, else
 // decodes straight into d_rows/d_scores/d_counts.
 int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
-                uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+                uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts,
+                const uint64_t** partials_out = nullptr, uint32_t* lists_out = nullptr) {
     ScanGeom g;
     int rc = plan_scan(ix, k, nq, &g);
     if (rc) return rc;
     const int ascending = (metric == CGVEC_L2);
     rc = ensure_parts(c, (size_t)nq * (g.grid > (uint32_t)ix->world ? g.grid : ix->world) * k);
     if (rc) return rc;
+    {
+        size_t need = (size_t)nq * g.grid * k;
+        if (need > c->scan_cap) {
+            size_t c0 = c->scan_cap, c1 = c->scan_cap;
+            rc = ensure(&c->d_scan[0], &c0, need); if (rc) return rc;
+            rc = ensure(&c->d_scan[1], &c1, need); if (rc) return rc;
+            c->scan_cap = c0 < c1 ? c0 : c1;
+        }
+    }
+    g.pdl = (uint32_t)ix->opt_pdl;
+    uint64_t* partials = c->d_scan[c->scan_flip & 1];
+    c->scan_flip++;
     ScanParams p = map_params(ix);
-    p.rows = ix->d_rows; p.norms = ix->d_norms; p.queries = d_q; p.partials = c->d_part[0];
+    p.rows = ix->d_rows; p.norms = ix->d_norms; p.queries = d_q; p.partials = partials;
     p.n_rows = ix->n; p.d = ix->dim; p.ld = ix->ld; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
     p.stages = g.stages; p.active_groups = g.groups; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
 
@@ -426,12 +481,43 @@ int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t
         ix->timed.emplace_back(e0, e1);
     }
     ix->last_geom = g;
-    return merge_lists(ix, c, c->d_part[0], nq, g.grid, k, ascending, local_keys, d_rows, d_scores, d_counts, st, (size_t)g.grid * k, k);
+    if (partials_out) { *partials_out = partials; *lists_out = g.grid; return CGVEC_OK; }   // caller fuses merge + exchange
+    return merge_lists(ix, c, partials, nq, g.grid, k, ascending, local_keys, d_rows, d_scores, d_counts, st, (size_t)g.grid * k, k);
 }
 
 int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
                uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
     if (ix->world == 1) return local_exact(ix, c, d_q, nq, k, metric, st, nullptr, d_rows, d_scores, d_counts);
+    if (ix->p2p && ix->opt_p2p && k <= kXchgMaxK && nq <= kXchgMaxQ) {
+        // merge + exchange + merge as one kernel over NVLink peer memory (exchange.cuh)
+        {
+            int arc = ensure_smem_attr(xchg_merge_kernel, 160 * 1024);
+            if (arc) return arc;
+        }
+        const uint64_t* partials = nullptr;
+        uint32_t lists = 0;
+        int rc = local_exact(ix, c, d_q, nq, k, metric, st, nullptr, nullptr, nullptr, nullptr, &partials, &lists);
+        if (rc) return rc;
+        if (lists <= 256) {
+            std::lock_guard<std::mutex> lk(ix->comm_mu);          // same step order on every rank
+            XchgParams xp{};
+            xp.partials = partials; xp.n_lists = lists; xp.k = k; xp.nq = nq; xp.ascending = (metric == CGVEC_L2);
+            xp.rank = (uint32_t)ix->rank; xp.world = (uint32_t)ix->world; xp.seq = ++ix->xseq;
+            for (int r = 0; r < ix->world; ++r) xp.peer[r] = ix->xpeer[r];
+            xp.out_rows = d_rows; xp.out_scores = d_scores; xp.out_counts = d_counts;
+            const size_t smem = ((size_t)lists * k + 9 * k) * 8;
+            xchg_merge_kernel<<<nq, kXchgThreads, smem, st>>>(xp);
+            ix->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return CGVEC_OK;
+        }
+        uint64_t* local_keys = nullptr;
+        rc = ensure_gather(ix, c, nq, k, &local_keys);
+        if (rc) return rc;
+        rc = merge_lists(ix, c, partials, nq, lists, k, metric == CGVEC_L2, local_keys, nullptr, nullptr, nullptr, st, (size_t)lists * k, k);
+        if (rc) return rc;
+        return exchange_and_decode(ix, c, local_keys, nq, k, metric == CGVEC_L2, st, d_rows, d_scores, d_counts);
+    }
     uint64_t* local_keys = nullptr;
     int rc = ensure_gather(ix, c, nq, k, &local_keys);
     if (rc) return rc;
@@ -454,7 +540,8 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 // 2-D fp16 tensor map, K (inner) x rows, 128-byte swizzle, box = 64 halves x box_rows, OOB reads as zero.
-int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows) {
+int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows,
+                  int l2promo = 1) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {inner, rows};
@@ -462,7 +549,9 @@ int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t r
     cuuint32_t box[2] = {(cuuint32_t)kTcKBlock, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B,
+                    l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CGVEC_OK;
 }
@@ -492,13 +581,11 @@ uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
 // re-run on the exact-order kernel.  Produces this shard's exact best-k keys (`local_keys` [nq][k]) or decoded results.
 int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
                  uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCap * 8);
-    });
-    if (attr_err != cudaSuccess) return fail(CGVEC_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(attr_err));
+    {
+        int arc = ensure_smem_attr(tc_scan_kernel, kSmemBudget);
+        if (!arc) arc = ensure_smem_attr(tc_select_kernel, kTcCap * 8);
+        if (arc) return arc;
+    }
     uint32_t stages = 0;
     const uint32_t n_max = tc_max_n(ix, &stages);
     if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
@@ -529,7 +616,7 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     CUDA_TRY(cudaGetLastError());
 
     CUtensorMap tmA, tmB;
-    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * 2, kTcTileRows); if (rc) return rc;
+    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * 2, kTcTileRows, ix->opt_tc_l2promo); if (rc) return rc;
     rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * 2, N); if (rc) return rc;
 
     TcParams p{};
@@ -537,26 +624,31 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     p.n_rows = n; p.norms = ix->d_norms; p.thr = d_thr; p.cand = c->d_cand; p.cand_count = d_cnt; p.overflow = d_overflow;
     p.cap = kTcCap; p.nq = nq; p.N = N; p.nkb = nkb; p.stages = stages; p.metric = METRIC_COSINE;
     p.tmem_cols = next_pow2(2 * N) < 32 ? 32 : next_pow2(2 * N);
+    p.prefetch_dist = (uint32_t)ix->opt_tc_prefetch;
     p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
     const uint32_t smem = tc_smem_layout(N, nkb, stages).total + 1024;
 
-    // geometric row ranges: after T rows the threshold sits at quantile kp/T, so the next range may hold
-    // about T*(cap/2 - kp)/kp rows before a list could reach cap/2 entries.
+    // geometric row ranges: after T rows the threshold sits at quantile kp/T, so a range of S rows adds about
+    // S*kp/T survivors; ranges are sized to keep each list near `target` entries (small sorts in tc_select_kernel)
+    // and never above cap (overflow -> exact-kernel fallback).
+    uint32_t target = ix->opt_tc_target > 0 ? (uint32_t)ix->opt_tc_target : 2048;
+    if (target < 4 * kp) target = 4 * kp;
+    if (target > kTcCap / 2) target = kTcCap / 2;
     uint64_t T = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
     while (T < n) {
-        uint64_t S = (T == 0) ? kTcCap : T * (kTcCap / 2 - kp) / kp;
+        uint64_t S = (T == 0) ? target : T * (target - kp) / kp;
         S = (S + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
         if (S < kTcTileRows) S = kTcTileRows;
-        if (T + S > n) S = n - T;
+        if (T + S > n || (n - T - S) * 8 < S) S = n - T;      // fold a small remainder into this range
         p.row_begin = T; p.row_end = T + S;
         uint64_t tiles = (S + kTcTileRows - 1) / kTcTileRows;
         uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
         tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
-        tc_select_kernel<<<nq, 256, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_thr, kTcCap, kp, kTcCap);
+        tc_select_kernel<<<nq, 1024, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_thr, kTcCap, kp, kTcCap);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
         T += S;
@@ -578,7 +670,7 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     rc = ensure_parts(c, (size_t)nq * kp * 2); if (rc) return rc;
     // sorted exact keys [nq][kp] (needed by the proof) ...
     uint64_t* sorted = c->d_part[1];
-    rc = merge_lists(ix, c, c->d_exact, nq, 1, kp, 0, sorted, nullptr, nullptr, nullptr, st, kp, kp, kp); if (rc) return rc;
+    rc = merge_lists(ix, c, c->d_exact, nq, 1, kp, 0, sorted, nullptr, nullptr, nullptr, st, kp, kp, kp, /*sorted_in=*/0); if (rc) return rc;
     const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f;
     tc_verify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c->d_cand, kTcCap, d_cnt, kp, sorted, want ? want : 1, d_na, d_rho, acc_bound, METRIC_COSINE, nq,
                                                       d_proven, d_overflow);
@@ -658,9 +750,64 @@ void drain_timings(Index* ix) {
     ix->timed.clear();
 }
 
+// Maps every rank's exchange buffer into this process (CUDA IPC over NVLink peer access).  Collective: all ranks call it.
+void setup_peer_exchange(Index* ix) {
+    ix->p2p = false;
+    if (ix->world > (int)kXchgMaxWorld) return;
+    bool ok = cudaMalloc(reinterpret_cast<void**>(&ix->xbuf), kXchgBytes) == cudaSuccess &&
+              cudaMemset(ix->xbuf, 0, kXchgBytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) ok = cudaIpcGetMemHandle(&mine, ix->xbuf) == cudaSuccess;
+    // all-gather (handle, ok) so that every rank takes the same decision
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<uint8_t> host(rec * ix->world, 0);
+    uint8_t* d_all = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&d_all), rec * ix->world) != cudaSuccess) { cudaGetLastError(); return; }
+    std::vector<uint8_t> me(rec, 0);
+    memcpy(me.data(), &mine, sizeof(mine));
+    me[sizeof(mine)] = ok ? 1 : 0;
+    cudaMemcpy(d_all + rec * ix->rank, me.data(), rec, cudaMemcpyHostToDevice);
+    bool gathered = nccl_api().AllGather(d_all + rec * ix->rank, d_all, rec, /*ncclUint8*/ 1, ix->comm, ix->main_stream) == kNcclSuccess &&
+                    cudaStreamSynchronize(ix->main_stream) == cudaSuccess &&
+                    cudaMemcpy(host.data(), d_all, rec * ix->world, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_all);
+    if (!gathered) { cudaGetLastError(); return; }
+    bool all_ok = true;
+    for (int r = 0; r < ix->world; ++r) all_ok = all_ok && host[rec * r + sizeof(mine)] == 1;
+    if (all_ok) {
+        for (int r = 0; r < ix->world && all_ok; ++r) {
+            if (r == ix->rank) { ix->xpeer[r] = ix->xbuf; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, &host[rec * r], sizeof(h));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = false; break; }
+            ix->xpeer[r] = static_cast<uint8_t*>(ptr);
+        }
+    }
+    // second agreement round: only use peer memory if EVERY rank mapped every peer
+    uint8_t* d_flag = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&d_flag), ix->world) != cudaSuccess) { cudaGetLastError(); return; }
+    uint8_t f = all_ok ? 1 : 0;
+    cudaMemcpy(d_flag + ix->rank, &f, 1, cudaMemcpyHostToDevice);
+    std::vector<uint8_t> flags(ix->world, 0);
+    bool g2 = nccl_api().AllGather(d_flag + ix->rank, d_flag, 1, 1, ix->comm, ix->main_stream) == kNcclSuccess &&
+              cudaStreamSynchronize(ix->main_stream) == cudaSuccess &&
+              cudaMemcpy(flags.data(), d_flag, ix->world, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_flag);
+    bool every = g2;
+    for (int r = 0; r < ix->world; ++r) every = every && flags[r] == 1;
+    ix->p2p = every;
+    if (!every) cudaGetLastError();
+}
+
 }  // namespace
 
 struct cgvec_index : Index {};
+
+namespace {
+#include "multi_device.inl"
+}  // namespace
 
 // ================================================================================================
 // lifecycle
@@ -693,6 +840,7 @@ static int create_common(uint32_t dim, cgvec_dtype storage, int device, int rank
         NcclUniqueId id;
         memcpy(&id, uid, sizeof(id));
         NCCL_TRY(nccl_api().CommInitRank(&ix->comm, world, id, rank));
+        setup_peer_exchange(ix.get());            // best effort: NCCL remains the transport if peer mapping fails
     }
     *out = ix.release();
     return CGVEC_OK;
@@ -700,8 +848,17 @@ static int create_common(uint32_t dim, cgvec_dtype storage, int device, int rank
 
 CGVEC_EXPORT int cgvec_create(uint32_t dim, cgvec_dtype storage, const int* device_ids, int n_devices, cgvec_index** out) {
     if (n_devices < 1) return fail(CGVEC_ERR_BAD_ARG, "n_devices must be >= 1");
-    if (n_devices > 1)
-        return fail(CGVEC_ERR_UNSUPPORTED, "single-process multi-device indexes are not built yet: use one cgvec_create_rank per GPU");
+    if (n_devices > 1) {
+        if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+        *out = nullptr;
+        if (dim == 0) return fail(CGVEC_ERR_BAD_DIM, "dimension must be > 0");
+        if (storage != CGVEC_F32 && storage != CGVEC_F16) return fail(CGVEC_ERR_BAD_ARG, "unknown storage dtype %d", (int)storage);
+        Index* mx = nullptr;
+        int rc = multi_create(dim, storage, device_ids, n_devices, &mx);
+        if (rc) return rc;
+        *out = static_cast<cgvec_index*>(mx);
+        return CGVEC_OK;
+    }
     return create_common(dim, storage, device_ids ? device_ids[0] : 0, 0, 1, nullptr, 0, out);
 }
 
@@ -721,10 +878,14 @@ CGVEC_EXPORT int cgvec_nccl_unique_id(void* out_128_bytes) {
 
 CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
     if (!ix) return CGVEC_OK;
+    if (!ix->parts.empty()) { multi_destroy(ix); return CGVEC_OK; }
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();
     drain_timings(ix);
     for (auto* c : ix->pool) ctx_free(c);
+    for (int r = 0; r < ix->world && r < (int)kXchgMaxWorld; ++r)
+        if (ix->xpeer[r] && r != ix->rank) cudaIpcCloseMemHandle(ix->xpeer[r]);
+    cudaFree(ix->xbuf);
     if (ix->comm) nccl_api().CommDestroy(ix->comm);
     cudaFree(ix->d_rows);
     cudaFree(ix->d_norms);
@@ -738,6 +899,7 @@ CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
 // ================================================================================================
 CGVEC_EXPORT int cgvec_reserve(cgvec_index* ix, uint64_t n_rows) {
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (!ix->parts.empty()) return multi_reserve(ix, n_rows);
     CUDA_TRY(cudaSetDevice(ix->device));
     return grow(ix, n_rows, /*exact=*/true);
 }
@@ -746,6 +908,7 @@ static int add_impl(cgvec_index* ix, const uint8_t (*ids)[16], const void* rows,
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (n == 0) return CGVEC_OK;
     if (!rows) return fail(CGVEC_ERR_BAD_ARG, "rows is NULL");
+    if (!ix->parts.empty()) return multi_add(ix, ids, rows, n, src_esize);
     if (src_esize != ix->esize)
         return fail(CGVEC_ERR_BAD_ARG, "index stores %s rows; use %s", ix->esize == 4 ? "f32" : "f16", ix->esize == 4 ? "cgvec_add" : "cgvec_add_f16");
     CUDA_TRY(cudaSetDevice(ix->device));
@@ -795,6 +958,10 @@ CGVEC_EXPORT int cgvec_add_f16(cgvec_index* ix, const uint8_t (*ids)[16], const 
 
 CGVEC_EXPORT int cgvec_normalize_rows(cgvec_index* ix) {
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (!ix->parts.empty()) {
+        for (Index* p : ix->parts) { int rc = cgvec_normalize_rows(static_cast<cgvec_index*>(p)); if (rc) return rc; }
+        return CGVEC_OK;
+    }
     if (!ix->n) return CGVEC_OK;
     CUDA_TRY(cudaSetDevice(ix->device));
     const int threads = 256;
@@ -812,6 +979,7 @@ CGVEC_EXPORT int cgvec_normalize_rows(cgvec_index* ix) {
 CGVEC_EXPORT int cgvec_fill_synthetic(cgvec_index* ix, uint64_t n, uint64_t seed, int unit_norm) {
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (!n) return CGVEC_OK;
+    if (!ix->parts.empty()) return multi_fill_synthetic(ix, n, seed, unit_norm);
     CUDA_TRY(cudaSetDevice(ix->device));
     uint64_t next = ix->n + n;
     if (ix->row_offset + next > 0xfffffffeull) return fail(CGVEC_ERR_UNSUPPORTED, "more than 2^32-2 rows are not supported");
@@ -872,6 +1040,7 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         return CGVEC_OK;
     }
     if (!queries) return fail(CGVEC_ERR_BAD_ARG, "queries is NULL");
+    if (!ix->parts.empty()) return multi_search(ix, queries, nq, k, o, out_rows, out_ids, out_scores, out_counts);
     CUDA_TRY(cudaSetDevice(ix->device));
     const uint64_t n_total_hint = ix->n;                       // local rows; sharded ranks may be empty individually
     if (ix->world == 1 && n_total_hint == 0) {
@@ -1048,6 +1217,7 @@ CGVEC_EXPORT int cgvec_get_row(const cgvec_index* cix, uint64_t local_row, float
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !out_row) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     if (local_row >= ix->n) return fail(CGVEC_ERR_NOT_FOUND, "row %llu out of range", (unsigned long long)local_row);
+    if (!ix->parts.empty()) return multi_get_rows(ix, local_row, 1, out_row);
     CUDA_TRY(cudaSetDevice(ix->device));
     const uint8_t* src = static_cast<const uint8_t*>(ix->d_rows) + local_row * (size_t)ix->ld * ix->esize;
     if (ix->dtype == CGVEC_F32) {
@@ -1076,6 +1246,7 @@ CGVEC_EXPORT int cgvec_get_rows(const cgvec_index* cix, uint64_t first, uint64_t
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (n == 0) return CGVEC_OK;
     if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    if (!ix->parts.empty()) return multi_get_rows(ix, first, n, out);
     if (first + n > ix->n) return fail(CGVEC_ERR_NOT_FOUND, "rows [%llu, %llu) out of range", (unsigned long long)first, (unsigned long long)(first + n));
     CUDA_TRY(cudaSetDevice(ix->device));
     const size_t pitch = (size_t)ix->ld * ix->esize;
@@ -1104,6 +1275,7 @@ CGVEC_EXPORT int cgvec_rescore(const cgvec_index* cix, const float* query, const
     if (n == 0) return CGVEC_OK;
     if (!query || !local_rows || !out_scores) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     if (formula != CGVEC_FORMULA_SIMD && metric == CGVEC_L2) return fail(CGVEC_ERR_UNSUPPORTED, "L2 exists in SIMD form only (simd_ops.rs:105-143)");
+    if (!ix->parts.empty()) return multi_rescore(ix, query, local_rows, n, metric, formula, out_scores);
     for (uint32_t i = 0; i < n; ++i)
         if (local_rows[i] >= ix->n) return fail(CGVEC_ERR_NOT_FOUND, "row %llu out of range", (unsigned long long)local_rows[i]);
     CUDA_TRY(cudaSetDevice(ix->device));
@@ -1137,6 +1309,11 @@ CGVEC_EXPORT int cgvec_distances_first(const cgvec_index* cix, const float* quer
     if (out_n) *out_n = m;
     if (m == 0) return CGVEC_OK;
     if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    if (!ix->parts.empty()) {                       // optimization.rs:404-418 form == the BASELINE formula of the first m rows
+        std::vector<uint64_t> rows(m);
+        for (uint64_t i = 0; i < m; ++i) rows[i] = i;
+        return multi_rescore(ix, query, rows.data(), (uint32_t)m, CGVEC_COSINE, CGVEC_FORMULA_BASELINE, out);
+    }
     CUDA_TRY(cudaSetDevice(ix->device));
     SearchCtx* c = nullptr;
     int rc = ctx_acquire(ix, &c);
@@ -1227,6 +1404,19 @@ CGVEC_EXPORT void cgvec_normalize_scores(float* s, size_t n) {       // search.r
 CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !out) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    if (!ix->parts.empty()) {
+        int rc = cgvec_get_stats(static_cast<const cgvec_index*>(ix->parts[0]), out);
+        if (rc) return rc;
+        out->rows = ix->n;
+        for (size_t s = 1; s < ix->parts.size(); ++s) {
+            cgvec_stats t;
+            rc = cgvec_get_stats(static_cast<const cgvec_index*>(ix->parts[s]), &t);
+            if (rc) return rc;
+            out->kernel_launches += t.kernel_launches;
+            out->bytes_resident += t.bytes_resident;
+        }
+        return CGVEC_OK;
+    }
     drain_timings(ix);
     memset(out, 0, sizeof(*out));
     out->kernel_launches = ix->launches.load();
@@ -1249,6 +1439,7 @@ CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
 
 CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t value) {
     if (!ix || !key) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    for (Index* part : ix->parts) { int rc = cgvec_set_option(static_cast<cgvec_index*>(part), key, value); if (rc) return rc; }
     std::string k(key);
     if (k == "tile_rows") ix->opt_tile_rows = (int)value;
     else if (k == "stages") ix->opt_stages = (int)value;
@@ -1258,10 +1449,15 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "timing") { ix->opt_timing = (int)value; if (!value) drain_timings(ix); }
     else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; }
     else if (k == "max_batch") ix->opt_max_nq = (int)value;
+    else if (k == "pdl") ix->opt_pdl = (int)value;
+    else if (k == "p2p") ix->opt_p2p = (int)value;
     else if (k == "tc_min_batch") ix->opt_tc_min_nq = (int)value;
     else if (k == "tc_stages") ix->opt_tc_stages = (int)value;
     else if (k == "tc_max_n") ix->opt_tc_max_n = (int)value;
     else if (k == "tc_margin") ix->opt_tc_margin = (int)value;
+    else if (k == "tc_target") ix->opt_tc_target = (int)value;
+    else if (k == "tc_l2promo") ix->opt_tc_l2promo = (int)value;
+    else if (k == "tc_prefetch") ix->opt_tc_prefetch = (int)value;
     else return fail(CGVEC_ERR_BAD_ARG, "unknown option '%s'", key);
     return CGVEC_OK;
 }

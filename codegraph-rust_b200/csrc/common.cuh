@@ -124,6 +124,32 @@ __device__ __forceinline__ float key_score(uint64_t key, bool ascending) {
 }
 __device__ __forceinline__ uint32_t key_row(uint64_t key) { return 0xffffffffu - static_cast<uint32_t>(key); }
 
+// Warp-wide maximum of 64-bit keys with two REDUX ops (hi word, then lo word among the lanes holding the max hi).
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+    const uint32_t hi = static_cast<uint32_t>(v >> 32), lo = static_cast<uint32_t>(v);
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return (static_cast<uint64_t>(mh) << 32) | ml;
+}
+
+// One warp pops the best `k` keys out of up to 32 DESCENDING-sorted lists held in shared memory (lane i owns
+// list i, `stride` keys apart, `len` keys long, 0 = end of list).  Keys are unique, so exactly one lane pops per
+// round.  Writes out[0..k) (0-padded) from lane 0.  ~60 cycles per round instead of a block-wide bitonic sort.
+__device__ __forceinline__ void warp_tournament_topk(const uint64_t* lists, uint32_t n_lists, uint32_t stride, uint32_t len,
+                                                     uint32_t k, uint64_t* out, uint32_t lane) {
+    const uint64_t* mine = lists + (size_t)lane * stride;
+    uint32_t ptr = 0;
+    uint64_t head = (lane < n_lists && len > 0) ? mine[0] : 0ull;
+    for (uint32_t r = 0; r < k; ++r) {
+        const uint64_t m = warp_max_u64(head);
+        if (lane == 0) out[r] = m;
+        if (m != 0ull && head == m) {
+            ++ptr;
+            head = ptr < len ? mine[ptr] : 0ull;
+        }
+    }
+}
+
 // Bitonic sort (descending) of n = 2^m keys in shared memory by `nthreads` threads that all call this
 // with the same arguments; `bar_id`/`nthreads` name the barrier they share.
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t* s, uint32_t n, uint32_t tid, uint32_t nthreads,

@@ -50,6 +50,7 @@ struct TcParams {
     uint32_t stages;
     uint32_t metric;            // METRIC_COSINE or METRIC_DOT
     uint32_t tmem_cols;         // power of two >= 2*N, >= 32
+    uint32_t prefetch_dist;     // K-blocks of L2 prefetch issued ahead of the demand loads (0 = off)
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
 };
@@ -75,6 +76,11 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
                  : "memory");
+}
+// L2 prefetch of one TMA box: keeps DRAM requests in flight far beyond what the shared-memory ring can hold
+// (the resident query block leaves only ~96 KB of stages), so the demand loads that follow mostly hit in L2.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -168,10 +174,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t pol = l2_policy_evict_first();
             mbar_arrive_expect_tx(b_bar, p.nkb * p.N * 128);
             for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.N * 128, &tmB, kb * kTcKBlock, 0, b_bar);
+            const uint64_t total_it = my_tiles * p.nkb;
+            auto prefetch_block = [&](uint64_t j) {
+                const uint64_t t = j / p.nkb;
+                const uint32_t kb = (uint32_t)(j - t * p.nkb);
+                tma_prefetch_2d(&tmA, kb * kTcKBlock, (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows));
+            };
+            for (uint64_t j = 0; j < p.prefetch_dist && j < total_it; ++j) prefetch_block(j);
             uint64_t it = 0;
             for (uint64_t t = 0; t < my_tiles; ++t) {
                 const int row0 = (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows);
                 for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
+                    if (p.prefetch_dist && it + p.prefetch_dist < total_it) prefetch_block(it + p.prefetch_dist);
                     const uint32_t s = it % p.stages;
                     if (it >= p.stages) mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
@@ -259,8 +273,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- between row ranges: keep each query's best kp candidates, publish the new threshold ---------------------
-// grid = nq, block = 256, dynamic smem = sort_cap * 8.  cand[q][0..count) -> sorted best kp in cand[q][0..kp).
-__global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count,
+// grid = nq, block = 1024, dynamic smem = sort_cap * 8.  cand[q][0..count) -> sorted best kp in cand[q][0..kp).
+__global__ void __launch_bounds__(1024) tc_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count,
                                                          float* __restrict__ thr, uint32_t cap, uint32_t kp, uint32_t sort_cap) {
     extern __shared__ __align__(16) uint64_t s_sel_keys[];
     uint64_t* s_keys = s_sel_keys;

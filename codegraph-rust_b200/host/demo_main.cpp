@@ -1,0 +1,61 @@
+// demo_main.cpp — drives the C++ host mirror end to end on the GPU and prints results for tests/test_host_cpp_gpu.py.
+// Embeddings come from the reference's deterministic text embedding (search.rs:178-205: djb2 + LCG + L2 normalise),
+// re-implemented here only to produce inputs the Python side can rebuild.
+#include <cmath>
+#include <iostream>
+
+#include "cgvec_host.hpp"
+
+static std::vector<float> hash_text_embedding(const std::string& text, size_t dimension) {
+    uint32_t h = 5381u;
+    for (unsigned char c : text) h = h * 33u + c;
+    std::vector<float> e(dimension);
+    uint32_t s = h;
+    for (size_t i = 0; i < dimension; ++i) {
+        s = s * 1103515245u + 12345u;
+        e[i] = (((float)s / 4294967296.0f) - 0.5f) * 2.0f;
+    }
+    float norm = 0.0f;
+    for (float x : e) norm = norm + x * x;
+    norm = std::sqrt(norm);
+    if (norm > 0.0f) for (float& x : e) x = x / norm;
+    return e;
+}
+
+int main(int argc, char** argv) {
+    const size_t n = argc > 1 ? std::stoul(argv[1]) : 2000, dim = argc > 2 ? std::stoul(argv[2]) : 384, limit = argc > 3 ? std::stoul(argv[3]) : 7;
+    try {
+        auto store = std::make_shared<cgvec::B200VectorStore>((uint32_t)dim);
+        std::vector<cgvec::CodeNode> nodes;
+        for (size_t i = 0; i < n; ++i) nodes.push_back({cgvec::NodeId::from_u64(i + 1), hash_text_embedding("fn item_" + std::to_string(i) + "() {}", dim)});
+        nodes.push_back({cgvec::NodeId::from_u64(999999), std::nullopt});          // skipped
+        store->store_embeddings(nodes);
+        std::cout << "len " << store->len() << "\n";
+        auto q = hash_text_embedding("fn item_42() { }", dim);
+        std::cout << "search_similar";
+        for (auto& id : store->search_similar(q, limit)) std::cout << " " << id.to_string();
+        std::cout << "\n";
+        std::cout << "top_k";
+        for (auto& [row, score] : store->top_k(q, limit)) std::cout << " " << row << ":" << std::hexfloat << score << std::defaultfloat;
+        std::cout << "\n";
+        auto backend = std::make_shared<cgvec::B200Backend>(store);
+        cgvec::SurrealVectorStore surreal(backend, 100);
+        std::cout << "surreal";
+        for (auto& id : surreal.search_similar(q, limit)) std::cout << " " << id.to_string();
+        std::cout << "\ncolumn " << backend->last_column << "\n";
+        cgvec::SemanticSearch sem(store);
+        std::cout << "semantic";
+        for (auto& r : sem.search_by_embedding(q, limit)) std::cout << " " << r.node_id.to_string() << ":" << std::hexfloat << r.score << std::defaultfloat;
+        std::cout << "\n";
+        auto missing = store->get_embedding(cgvec::NodeId::from_u64(123456789));
+        std::cout << "missing " << (missing ? "some" : "none") << "\n";
+        try {
+            store->search_similar(std::vector<float>(dim + 1, 1.0f), 3);
+            std::cout << "baddim no-error\n";
+        } catch (const cgvec::Error& e) { std::cout << "baddim " << e.code << "\n"; }
+    } catch (const cgvec::Error& e) {
+        std::cout << "error " << e.code << " " << e.what() << "\n";
+        return e.code == CGVEC_ERR_NO_DEVICE ? 3 : 1;
+    }
+    return 0;
+}

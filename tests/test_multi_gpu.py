@@ -66,3 +66,46 @@ def test_sharded_search_equals_oracle(oracle, metric_name):
                 assert gc[qi] == k
                 assert gr[qi] == wi.tolist()
                 assert np.frombuffer(gs, np.float32).reshape(3, k)[qi].tobytes() == ws.tobytes()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("dtype_name", ["f32", "f16"])
+def test_single_process_multi_device_index(cg, oracle, dtype_name):
+    """cgvec_create(n_devices > 1): one host process drives every GPU (the Rust-server deployment).  Rows are dealt in
+    1024-row blocks round-robin; results, ids, get_embedding, rescore and upserts must match a single index."""
+    import uuid
+    G = min(_ngpus(), 4)
+    dt = cg.F32 if dtype_name == "f32" else cg.F16
+    rng = np.random.default_rng(41)
+    n, d = 7_777, 192
+    rows = (rng.standard_normal((n, d)) / 14).astype(np.float32)
+    rows[7_000] = rows[9]                                     # tie across shards
+    ref = rows if dt == cg.F32 else rows.astype(np.float16).astype(np.float32)
+    ids = [uuid.UUID(int=i + 1) for i in range(n)]
+    ix = cg.Index(d, dt, devices=list(range(G)))
+    ix.add(rows[:3000], ids[:3000]); ix.add(rows[3000:], ids[3000:])          # incremental adds cross block boundaries
+    assert len(ix) == n
+    qs = rng.standard_normal((6, d)).astype(np.float32)
+    qs[0] = rows[9]
+    for metric, om in ((cg.COSINE, oracle.COSINE), (cg.L2, oracle.L2), (cg.DOT, oracle.DOT)):
+        r, s, c, got_ids = ix.search(qs, 25, metric, want_ids=True)
+        for qi in range(len(qs)):
+            wi, ws = oracle.parallel_top_k_search(qs[qi], ref, 25, metric=om)
+            assert r[qi].tolist() == wi.tolist()
+            assert s[qi].tobytes() == ws.tobytes()
+            assert [uuid.UUID(bytes=got_ids[qi, j].tobytes()).int - 1 for j in range(25)] == wi.tolist()
+    assert ix.get_rows(1000, 2500).tobytes() == ref[1000:3500].tobytes()
+    assert ix.get(ids[5000]).tobytes() == ref[5000].tobytes()
+    sel = np.array([0, 1023, 1024, 2048, 7776], np.uint64)
+    assert ix.rescore(qs[1], sel, cg.COSINE, cg.FORMULA_SEQ).tobytes() == np.float32([oracle.cosine_similarity_seq(qs[1], ref[int(i)]) for i in sel]).tobytes()
+    assert ix.distances_first(qs[2], 1500).tobytes() == oracle.compute_distances_cpu(qs[2], ref.reshape(-1), d, 1500).tobytes()
+    ix.add(-rows[9:10], [ids[9]])                              # upsert by id
+    assert len(ix) == n and ix.search(qs[0], 1)[0][0, 0] == 7_000
+    with pytest.raises(cg.CgvecError):
+        ix.search(qs, 500)                                     # beyond the peer-exchange k limit
+    ix.close()
+    # device-generated synthetic rows are the same matrix whatever the sharding
+    a = cg.Index(d, dt, devices=list(range(G))); a.fill_synthetic(5000, 77, True)
+    b = cg.Index(d, dt); b.fill_synthetic(5000, 77, True)
+    assert a.get_rows(0, 5000).tobytes() == b.get_rows(0, 5000).tobytes()
+    a.close(); b.close()
