@@ -36,7 +36,7 @@ EXPORTS = [
     "cgvec_create", "cgvec_create_rank", "cgvec_nccl_unique_id", "cgvec_destroy", "cgvec_reserve", "cgvec_add",
     "cgvec_add_f16", "cgvec_normalize_rows", "cgvec_fill_synthetic", "cgvec_len", "cgvec_dim", "cgvec_search",
     "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
-    "cgvec_shard_range", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
+    "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
     "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_last_error", "cgvec_version",
 ]
 
@@ -100,6 +100,11 @@ def load_library(build: bool = True):
     L.cgvec_row_of_id.argtypes = [vp, vp, u64p]
     L.cgvec_rescore.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp]
     L.cgvec_distances_first.argtypes = [vp, vp, C.c_uint64, vp, u64p]
+    L.cgvec_quantize_i8.argtypes = [vp]
+    L.cgvec_get_codes_i8.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.cgvec_search_i8.argtypes = [vp, vp, C.c_uint32, vp, vp, u32p]
+    L.cgvec_save_flat.argtypes = [vp, C.c_char_p]
+    L.cgvec_load_flat.argtypes = [vp, C.c_char_p, u64p]
     L.cgvec_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
     L.cgvec_merge_topk_host.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, u32p]
     L.cgvec_prefetch_k_basic.argtypes = [C.c_uint64]; L.cgvec_prefetch_k_basic.restype = C.c_uint64
@@ -267,6 +272,33 @@ class Index:
         n = C.c_uint64()
         _check(load_library().cgvec_distances_first(self._h, _ptr(q), limit, _ptr(out), C.byref(n)))
         return out[: n.value].copy()
+
+    def quantize_i8(self):
+        """ModelOptimizer::quantize_batch, 8 bits (optimization.rs:212-224, 268-274)."""
+        _check(load_library().cgvec_quantize_i8(self._h))
+
+    def codes_i8(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), np.uint8)
+        _check(load_library().cgvec_get_codes_i8(self._h, first, n, _ptr(out)))
+        return out
+
+    def search_optimized(self, query, limit: int):
+        """OptimizationResult::search_optimized (optimization.rs:63-150) -> (rows, scores)."""
+        q = np.ascontiguousarray(query, np.float32)
+        k = max(int(limit), 1)
+        rows = np.empty(k, np.uint64); scores = np.empty(k, np.float32); cnt = C.c_uint32()
+        _check(load_library().cgvec_search_i8(self._h, _ptr(q), limit, _ptr(rows), _ptr(scores), C.byref(cnt)))
+        return rows[: cnt.value].copy(), scores[: cnt.value].copy()
+
+    def save_flat(self, path: str):
+        """memory.rs:241-310 save_to_mmap format."""
+        _check(load_library().cgvec_save_flat(self._h, path.encode()))
+
+    def load_flat(self, path: str) -> int:
+        """memory.rs:312-374 load_from_mmap format; appends the rows."""
+        n = C.c_uint64()
+        _check(load_library().cgvec_load_flat(self._h, path.encode(), C.byref(n)))
+        return int(n.value)
 
     def stats(self) -> Stats:
         s = Stats()

@@ -20,6 +20,7 @@
 #include "exchange.cuh"
 #include "nccl_dyn.h"
 #include "scan_exact.cuh"
+#include "scan_i8.cuh"
 #include "scan_tc.cuh"
 
 #define CGVEC_EXPORT extern "C" __attribute__((visibility("default")))
@@ -121,6 +122,11 @@ struct Index {
     void* d_rows = nullptr;
     float* d_norms = nullptr;
     uint64_t n = 0, cap = 0;
+    // int8 quantised copy (scan_i8.cuh), built by cgvec_quantize_i8
+    uint8_t* d_codes = nullptr;
+    int32_t* d_inorms = nullptr;
+    uint64_t n_codes = 0;
+    uint32_t ld8 = 0;
 
     std::vector<uint8_t> ids;     // 16 bytes per local row
     std::vector<uint8_t> has_id;  // 1 per local row
@@ -142,7 +148,7 @@ struct Index {
     // knobs (cgvec_set_option)
     int opt_tile_rows = 0, opt_stages = 0, opt_sync = 0, opt_l2_hint = 0, opt_grid = 0, opt_timing = 0, opt_max_nq = kScanMaxQ;
     int opt_pdl = 1;
-    int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 16;
+    int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 0, opt_tc_first = 0, opt_tc_kernel = 0, opt_tc_debug = 0, opt_tc2_max_n = kTc2MaxN;
     int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0;
     std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
 
@@ -562,7 +568,7 @@ bool tensor_path_applicable(const Index* ix, int metric, uint32_t nq) {
     return ix->dtype == CGVEC_F16 && metric == CGVEC_COSINE && nq >= 1 && ix->n >= 1;
 }
 
-// Largest MMA N (multiple of 16) whose resident query block leaves >= 3 row stages in shared memory.
+// Largest MMA N (multiple of 16) whose resident query block leaves >= 3 row stages in shared memory (tc_scan_kernel).
 uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
     const uint32_t nkb = (ix->dim + kTcKBlock - 1) / kTcKBlock;
     uint32_t limit = (uint32_t)ix->opt_tc_max_n;
@@ -575,6 +581,22 @@ uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
     }
     return 0;
 }
+// tc2_scan_kernel (CTA pairs) streams the query block: any N <= 256 fits; stages follow from N.
+uint32_t tc2_stages(const Index* ix, uint32_t N) {
+    for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 12; s >= 2; --s)
+        if (tc2_smem_layout(N, s).total + 1024 <= kSmemBudget) return s;
+    return 0;
+}
+// which kernel serves a batch of nq queries, and how many queries one pass may take
+bool tc_use_pairs(const Index* ix, uint32_t nq) {
+    if (ix->opt_tc_kernel == 1) return false;
+    if (ix->opt_tc_kernel == 2) return true;
+    return nq > tc_max_n(ix, nullptr);
+}
+uint32_t tc_batch_limit(const Index* ix, uint32_t nq) {
+    if (tc_use_pairs(ix, nq)) { uint32_t m = (uint32_t)ix->opt_tc2_max_n & ~15u; return m >= 16 && m <= kTc2MaxN ? m : kTc2MaxN; }
+    return tc_max_n(ix, nullptr);
+}
 
 // Tensor-core scan of the local shard for `nq` <= N_max queries (f32, on the device, stride qstride): approximate
 // ordering on tcgen05, exact re-score of the kp survivors per query, proof of exactness; unproven queries are
@@ -583,18 +605,24 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
                  uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
     {
         int arc = ensure_smem_attr(tc_scan_kernel, kSmemBudget);
+        if (!arc) arc = ensure_smem_attr(tc2_scan_kernel, kSmemBudget);
         if (!arc) arc = ensure_smem_attr(tc_select_kernel, kTcCap * 8);
         if (arc) return arc;
     }
+    const bool pairs = tc_use_pairs(ix, nq);
     uint32_t stages = 0;
-    const uint32_t n_max = tc_max_n(ix, &stages);
+    const uint32_t n_max = pairs ? kTc2MaxN : tc_max_n(ix, &stages);
     if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
     const uint32_t N = (nq + 15) & ~15u;
     const uint32_t nkb = (ix->dim + kTcKBlock - 1) / kTcKBlock, dpad = nkb * kTcKBlock;
-    {   // more stages when the query block is small
+    if (pairs) {
+        stages = tc2_stages(ix, N);
+        if (stages < 2) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the paired tensor kernel at N = %u", N);
+    } else {   // more stages when the query block is small
         for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s)
             if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { stages = s; break; }
     }
+    const uint32_t tile_rows = pairs ? 2 * kTcTileRows : kTcTileRows;
     const uint64_t n = ix->n;
     const uint32_t want = (uint32_t)(k < n ? k : n);
     uint32_t kp = k + (ix->opt_tc_margin > 0 ? (uint32_t)ix->opt_tc_margin : (k / 2 > 32 ? k / 2 : 32));
@@ -603,13 +631,13 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
 
     int rc;
     rc = ensure(&c->d_B, &c->B_cap, (size_t)N * dpad); if (rc) return rc;
-    rc = ensure(&c->d_tc_f, &c->tcf_cap, (size_t)3 * kTcMaxN); if (rc) return rc;
-    rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)2 * kTcMaxN + 4); if (rc) return rc;
-    rc = ensure(&c->d_cand, &c->cand_cap, (size_t)kTcMaxN * kTcCap); if (rc) return rc;
-    rc = ensure(&c->d_exact, &c->exact_cap, (size_t)kTcMaxN * (kTcCap / 8)); if (rc) return rc;
-    rc = ensure(&c->h_proven, &c->hprov_cap, (size_t)kTcMaxN + 4, true); if (rc) return rc;
-    float *d_thr = c->d_tc_f, *d_na = c->d_tc_f + kTcMaxN, *d_rho = c->d_tc_f + 2 * kTcMaxN;
-    uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTcMaxN, *d_overflow = c->d_tc_u + 2 * kTcMaxN;
+    rc = ensure(&c->d_tc_f, &c->tcf_cap, (size_t)3 * kTc2MaxN); if (rc) return rc;
+    rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)2 * kTc2MaxN + 4); if (rc) return rc;
+    rc = ensure(&c->d_cand, &c->cand_cap, (size_t)kTc2MaxN * kTcCap); if (rc) return rc;
+    rc = ensure(&c->d_exact, &c->exact_cap, (size_t)kTc2MaxN * (kTcCap / 8)); if (rc) return rc;
+    rc = ensure(&c->h_proven, &c->hprov_cap, (size_t)kTc2MaxN + 4, true); if (rc) return rc;
+    float *d_thr = c->d_tc_f, *d_na = c->d_tc_f + kTc2MaxN, *d_rho = c->d_tc_f + 2 * kTc2MaxN;
+    uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTc2MaxN, *d_overflow = c->d_tc_u + 2 * kTc2MaxN;
 
     tc_prep_queries_kernel<<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, c->d_B, d_na, d_rho, d_thr, d_cnt, d_overflow);
     ix->launches++;
@@ -617,7 +645,7 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
 
     CUtensorMap tmA, tmB;
     rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * 2, kTcTileRows, ix->opt_tc_l2promo); if (rc) return rc;
-    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * 2, N); if (rc) return rc;
+    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * 2, pairs ? N / 2 : N); if (rc) return rc;
 
     TcParams p{};
     ScanParams map = map_params(ix);
@@ -625,27 +653,35 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     p.cap = kTcCap; p.nq = nq; p.N = N; p.nkb = nkb; p.stages = stages; p.metric = METRIC_COSINE;
     p.tmem_cols = next_pow2(2 * N) < 32 ? 32 : next_pow2(2 * N);
     p.prefetch_dist = (uint32_t)ix->opt_tc_prefetch;
+    p.debug = (uint32_t)ix->opt_tc_debug;
     p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
-    const uint32_t smem = tc_smem_layout(N, nkb, stages).total + 1024;
+    const uint32_t smem = (pairs ? tc2_smem_layout(N, stages).total : tc_smem_layout(N, nkb, stages).total) + 1024;
 
     // geometric row ranges: after T rows the threshold sits at quantile kp/T, so a range of S rows adds about
     // S*kp/T survivors; ranges are sized to keep each list near `target` entries (small sorts in tc_select_kernel)
     // and never above cap (overflow -> exact-kernel fallback).
-    uint32_t target = ix->opt_tc_target > 0 ? (uint32_t)ix->opt_tc_target : 2048;
+    uint32_t target = ix->opt_tc_target > 0 ? (uint32_t)ix->opt_tc_target : 1024;
     if (target < 4 * kp) target = 4 * kp;
     if (target > kTcCap / 2) target = kTcCap / 2;
     uint64_t T = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
     while (T < n) {
-        uint64_t S = (T == 0) ? target : T * (target - kp) / kp;
-        S = (S + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
-        if (S < kTcTileRows) S = kTcTileRows;
+        uint64_t S = (T == 0) ? (ix->opt_tc_first > 0 ? (uint64_t)ix->opt_tc_first : target) : T * (target - kp) / kp;
+        if (T == 0 && S > kTcCap) S = kTcCap;
+        S = (S + tile_rows - 1) / tile_rows * tile_rows;
+        if (S < tile_rows) S = tile_rows;
         if (T + S > n || (n - T - S) * 8 < S) S = n - T;      // fold a small remainder into this range
         p.row_begin = T; p.row_end = T + S;
-        uint64_t tiles = (S + kTcTileRows - 1) / kTcTileRows;
-        uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
-        tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+        uint64_t tiles = (S + tile_rows - 1) / tile_rows;
+        if (pairs) {
+            const uint64_t max_pairs = (uint64_t)ix->sm_count / 2;
+            uint32_t grid = 2 * (uint32_t)(tiles < max_pairs ? tiles : max_pairs);
+            tc2_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+        } else {
+            uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
+            tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+        }
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
         tc_select_kernel<<<nq, 1024, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_thr, kTcCap, kp, kTcCap);
@@ -712,7 +748,7 @@ int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uin
     } else if (path == CGVEC_PATH_AUTO) {
         tensor = tensor_path_applicable(ix, metric, nq) && nq >= (uint32_t)ix->opt_tc_min_nq && ix->n >= 4 * kTcCap && k <= kTcCap / 16;
     }
-    uint32_t n_max = tensor ? tc_max_n(ix, nullptr) : 0;
+    uint32_t n_max = tensor ? tc_batch_limit(ix, nq) : 0;
     if (tensor && n_max == 0) {
         if (path == CGVEC_PATH_TENSOR) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
         tensor = false;
@@ -889,6 +925,8 @@ CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
     if (ix->comm) nccl_api().CommDestroy(ix->comm);
     cudaFree(ix->d_rows);
     cudaFree(ix->d_norms);
+    cudaFree(ix->d_codes);
+    cudaFree(ix->d_inorms);
     if (ix->main_stream) cudaStreamDestroy(ix->main_stream);
     delete ix;
     return CGVEC_OK;
@@ -1339,6 +1377,176 @@ CGVEC_EXPORT int cgvec_distances_first(const cgvec_index* cix, const float* quer
 }
 
 // ================================================================================================
+// int8 quantised scan: quantize_batch (optimization.rs:212-224,268-274) + search_optimized (:63-150)
+// ================================================================================================
+CGVEC_EXPORT int cgvec_quantize_i8(cgvec_index* ix) {
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    if (!ix->parts.empty() || ix->world > 1) return fail(CGVEC_ERR_UNSUPPORTED, "the int8 scan serves single-GPU indexes");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    cudaFree(ix->d_codes); cudaFree(ix->d_inorms);
+    ix->d_codes = nullptr; ix->d_inorms = nullptr; ix->n_codes = 0;
+    ix->ld8 = (ix->dim + 15) & ~15u;
+    if (ix->n == 0) return CGVEC_OK;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ix->d_codes), ix->n * (size_t)ix->ld8));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ix->d_inorms), ix->n * sizeof(int32_t)));
+    const int threads = 256;
+    const uint64_t blocks = (ix->n * 32 + threads - 1) / threads;
+    if (ix->dtype == CGVEC_F32)
+        quantize_rows_i8_kernel<float><<<(unsigned)blocks, threads, 0, ix->main_stream>>>(static_cast<const float*>(ix->d_rows), ix->n, ix->dim, ix->ld, ix->ld8, ix->d_codes, ix->d_inorms);
+    else
+        quantize_rows_i8_kernel<__half><<<(unsigned)blocks, threads, 0, ix->main_stream>>>(static_cast<const __half*>(ix->d_rows), ix->n, ix->dim, ix->ld, ix->ld8, ix->d_codes, ix->d_inorms);
+    ix->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    ix->n_codes = ix->n;
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_get_codes_i8(const cgvec_index* cix, uint64_t first, uint64_t n, uint8_t* out) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || (!out && n)) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    if (first + n > ix->n_codes) return fail(CGVEC_ERR_NOT_FOUND, "codes [%llu, %llu) out of range (call cgvec_quantize_i8 first)", (unsigned long long)first, (unsigned long long)(first + n));
+    if (!n) return CGVEC_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    CUDA_TRY(cudaMemcpy2D(out, ix->dim, ix->d_codes + first * ix->ld8, ix->ld8, ix->dim, n, cudaMemcpyDeviceToHost));
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_search_i8(const cgvec_index* cix, const float* query, uint32_t limit, uint64_t* out_rows, float* out_scores,
+                                 uint32_t* out_count) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || !query) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    if (out_count) *out_count = 0;
+    uint32_t k = limit < 1 ? 1 : limit;                         // optimization.rs:64 `_limit.max(1)`
+    if (ix->n_codes == 0) return CGVEC_OK;                       // :70-72 empty -> empty
+    if (k > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "limit = %u exceeds the fused top-k limit of %u", k, kMaxK);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    SearchCtx* c = nullptr;
+    int rc = ctx_acquire(ix, &c);
+    if (rc) return rc;
+    auto done = [&](int code) { ctx_release(ix, c); return code; };
+    cudaStream_t st = c->stream;
+    const uint32_t ld8 = ix->ld8;
+    rc = ensure(&c->d_q, &c->q_cap, (size_t)ix->dim + ld8 / 4 + 16); if (rc) return done(rc);
+    int8_t* d_q8 = reinterpret_cast<int8_t*>(c->d_q + ((ix->dim + 3) & ~3u));
+    float* d_qn = reinterpret_cast<float*>(d_q8 + ld8);
+    int32_t* d_qs = reinterpret_cast<int32_t*>(d_qn + 1);
+    cudaError_t e = cudaMemcpyAsync(c->d_q, query, ix->dim * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e)));
+    quantize_query_i8_kernel<<<1, 256, 0, st>>>(c->d_q, ix->dim, ld8, d_q8, d_qn, d_qs);
+    ix->launches++;
+    const uint32_t sync = 8, rows_per_iter = (kI8Threads / 32) * kI8RowsPerWarp;
+    uint32_t cand = next_pow2(k + sync * rows_per_iter);
+    if (cand < 64) cand = 64;
+    const uint64_t groups = (ix->n_codes + rows_per_iter - 1) / rows_per_iter;
+    uint32_t grid = (uint32_t)ix->sm_count * 4;
+    if (groups < grid) grid = (uint32_t)groups;
+    rc = ensure_parts(c, (size_t)grid * k); if (rc) return done(rc);
+    {
+        size_t need = (size_t)grid * k;
+        if (need > c->scan_cap) {
+            size_t c0 = c->scan_cap, c1 = c->scan_cap;
+            rc = ensure(&c->d_scan[0], &c0, need); if (rc) return done(rc);
+            rc = ensure(&c->d_scan[1], &c1, need); if (rc) return done(rc);
+            c->scan_cap = c0 < c1 ? c0 : c1;
+        }
+    }
+    I8Params p{};
+    p.codes = ix->d_codes; p.norms = ix->d_inorms; p.q = d_q8; p.q_norm = d_qn; p.q_sum = d_qs; p.partials = c->d_scan[0];
+    p.n_rows = ix->n_codes; p.ld8 = ld8; p.k = k; p.cand_cap = cand; p.sync_interval = sync;
+    const size_t smem = ((ld8 + 15) & ~15u) + (size_t)cand * 8;
+    rc = ensure_smem_attr(scan_i8_kernel, 96 * 1024); if (rc) return done(rc);
+    scan_i8_kernel<<<grid, kI8Threads, smem, st>>>(p);
+    ix->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "scan_i8 launch failed: %s", cudaGetErrorString(e)));
+    {
+        size_t oc = c->out_cap, oc2 = c->out_cap;
+        rc = ensure(&c->d_rows, &oc, (size_t)k); if (rc) return done(rc);
+        rc = ensure(&c->d_scores, &oc2, (size_t)k); if (rc) return done(rc);
+        c->out_cap = oc < oc2 ? oc : oc2;
+        rc = ensure(&c->d_counts, &c->cnt_cap, 4); if (rc) return done(rc);
+    }
+    rc = merge_lists(ix, c, c->d_scan[0], 1, grid, k, 0, nullptr, c->d_rows, c->d_scores, c->d_counts, st, (size_t)grid * k, k);
+    if (rc) return done(rc);
+    std::vector<uint64_t> rows(k);
+    std::vector<float> scores(k);
+    uint32_t cnt = 0;
+    e = cudaMemcpyAsync(rows.data(), c->d_rows, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores.data(), c->d_scores, k * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, c->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "int8 search failed: %s", cudaGetErrorString(e)));
+    float qn = 0.0f;
+    cudaMemcpy(&qn, d_qn, sizeof(float), cudaMemcpyDeviceToHost);
+    if (qn == 0.0f) cnt = 0;                                      // optimization.rs:113-115: zero query -> empty
+    for (uint32_t i = 0; i < cnt; ++i) { if (out_rows) out_rows[i] = rows[i]; if (out_scores) out_scores[i] = scores[i]; }
+    if (out_count) *out_count = cnt;
+    ix->searches++;
+    return done(CGVEC_OK);
+}
+
+// ================================================================================================
+// flat matrix file: MemoryOptimizer::save_to_mmap / load_from_mmap, codegraph-vector/src/memory.rs:241-374
+//   [u64 vector_count][u64 dimension][vector_count * dimension f32, row-major], native endian, exact file size
+// ================================================================================================
+CGVEC_EXPORT int cgvec_save_flat(const cgvec_index* cix, const char* path) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || !path) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CGVEC_ERR_BAD_ARG, "Failed to create mmap file: %s", path);
+    uint64_t hdr[2] = {ix->n, ix->dim};
+    bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1;
+    const uint64_t chunk = 1u << 16;
+    std::vector<float> buf;
+    for (uint64_t r = 0; ok && r < ix->n; r += chunk) {
+        uint64_t m = ix->n - r < chunk ? ix->n - r : chunk;
+        buf.resize((size_t)m * ix->dim);
+        int rc = cgvec_get_rows(cix, r, m, buf.data());      // widens f16 storage exactly
+        if (rc) { fclose(f); return rc; }
+        ok = fwrite(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(CGVEC_ERR_BAD_ARG, "Failed to write to file: %s", path);
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_load_flat(cgvec_index* ix, const char* path, uint64_t* out_rows_loaded) {
+    if (!ix || !path) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(CGVEC_ERR_BAD_ARG, "Failed to open mmap file: %s", path);
+    auto bail = [&](int code) { fclose(f); return code; };
+    uint64_t hdr[2];
+    if (fseek(f, 0, SEEK_END) != 0) return bail(fail(CGVEC_ERR_BAD_ARG, "Failed to seek in file"));
+    const long long size = ftell(f);
+    rewind(f);
+    if (size < (long long)sizeof(hdr) || fread(hdr, sizeof(hdr), 1, f) != 1) return bail(fail(CGVEC_ERR_BAD_ARG, "Invalid mmap file: too small"));   // memory.rs:322-326
+    if (hdr[1] != ix->dim) return bail(fail(CGVEC_ERR_BAD_DIM, "Dimension mismatch: expected %u, found %llu", ix->dim, (unsigned long long)hdr[1]));      // :333-338
+    const unsigned long long expect = sizeof(hdr) + (unsigned long long)hdr[0] * hdr[1] * sizeof(float);
+    if ((unsigned long long)size != expect) return bail(fail(CGVEC_ERR_BAD_ARG, "Invalid mmap file size: expected %llu, got %lld", expect, size));       // :345-351
+    int rc = cgvec_reserve(ix, ix->n + hdr[0]);
+    if (rc) return bail(rc);
+    const uint64_t chunk = 1u << 16;
+    std::vector<float> buf;
+    std::vector<uint16_t> half;
+    for (uint64_t r = 0; r < hdr[0]; r += chunk) {
+        uint64_t m = hdr[0] - r < chunk ? hdr[0] - r : chunk;
+        buf.resize((size_t)m * ix->dim);
+        if (fread(buf.data(), sizeof(float), buf.size(), f) != buf.size()) return bail(fail(CGVEC_ERR_BAD_ARG, "Failed to read matrix data"));
+        if (ix->dtype == CGVEC_F32) rc = cgvec_add(ix, nullptr, buf.data(), m);
+        else {
+            half.resize(buf.size());
+            for (size_t i = 0; i < buf.size(); ++i) half[i] = __half_as_ushort(__float2half_rn(buf[i]));
+            rc = cgvec_add_f16(ix, nullptr, half.data(), m);
+        }
+        if (rc) return bail(rc);
+    }
+    fclose(f);
+    if (out_rows_loaded) *out_rows_loaded = hdr[0];
+    return CGVEC_OK;
+}
+
+// ================================================================================================
 // host-side helpers (pure CPU)
 // ================================================================================================
 CGVEC_EXPORT int cgvec_shard_range(uint64_t n, int world, int rank, uint64_t* begin, uint64_t* end) {
@@ -1458,6 +1666,10 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "tc_target") ix->opt_tc_target = (int)value;
     else if (k == "tc_l2promo") ix->opt_tc_l2promo = (int)value;
     else if (k == "tc_prefetch") ix->opt_tc_prefetch = (int)value;
+    else if (k == "tc_first") ix->opt_tc_first = (int)value;
+    else if (k == "tc_kernel") ix->opt_tc_kernel = (int)value;
+    else if (k == "tc_debug") ix->opt_tc_debug = (int)value;
+    else if (k == "tc2_max_n") ix->opt_tc2_max_n = (int)value;
     else return fail(CGVEC_ERR_BAD_ARG, "unknown option '%s'", key);
     return CGVEC_OK;
 }

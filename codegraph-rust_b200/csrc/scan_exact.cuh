@@ -15,7 +15,7 @@
 // The row's squared norm (a function of the row only) is computed once at store time in the same
 // order (norms.cuh) — the scan issues one FFMA per matrix element.
 //
-// Data movement.  Persistent CTAs (one per SM).  Warp 0 is the producer: for every tile of `tile_rows`
+// Data movement.  Persistent CTAs (one per SM).  The last warp is the producer: for every tile of `tile_rows`
 // rows it arms an mbarrier and issues one cp.async.bulk (TMA engine, SASS UBLKCP) per row into a
 // ring of `stages` shared-memory buffers; rows land with a padded stride (row_words = 8 mod 16 words)
 // so the 4 rows a consumer warp reads concurrently fall in disjoint bank octets -> conflict-free
@@ -217,8 +217,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
     }
     __syncthreads();
 
-    if (warp == 0) {
+    if (warp == kScanConsumerWarps) {
         // ===================== producer: TMA-engine bulk copies, one per row =====================
+        // (the last warp: the SM's arbiter favours higher warp ids, and this warp must never wait for an issue slot)
         const uint64_t policy = l2_policy_evict_first();
         if (lane == 0) {
             mbar_arrive_expect_tx(q_bar, NQ * qstride * 4);
@@ -243,9 +244,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
         }
     } else {
         // ===================== consumers: exact-order scoring + candidate filter =====================
-        const uint32_t cw = warp - 1;
+        const uint32_t cw = warp;
         const uint32_t group = cw / warps_per_stage, sub = cw % warps_per_stage;
-        const uint32_t ctid = tid - 32, nct = kScanConsumerWarps * 32;
+        const uint32_t ctid = tid, nct = kScanConsumerWarps * 32;
         const int L = lane & 7;
         const uint32_t lrow = sub * 4 + (lane >> 3);             // row of the tile this octet scores
 

@@ -148,6 +148,21 @@ int cgvec_rescore(const cgvec_index* idx, const float* query, const uint64_t* lo
  * cosine DISTANCE (optimization.rs:404-418 form) of the first `limit` stored rows. Returns count in *out_n. */
 int cgvec_distances_first(const cgvec_index* idx, const float* query, uint64_t limit, float* out, uint64_t* out_n);
 
+/* ---- int8 quantised scan: ModelOptimizer::quantize_batch + OptimizationResult::search_optimized
+ * (codegraph-vector/src/optimization.rs:63-150, :212-224, :268-274).  cgvec_quantize_i8 builds u8 codes (value + 128)
+ * of the currently stored rows; cgvec_search_i8 returns up to max(limit,1) rows by the int8 cosine, best first
+ * (ties -> lower row), with scores bit-identical to the reference's f32 expression.  Single-GPU indexes. */
+int cgvec_quantize_i8(cgvec_index* idx);
+int cgvec_get_codes_i8(const cgvec_index* idx, uint64_t first_row, uint64_t n, uint8_t* out /* n x dim */);
+int cgvec_search_i8(const cgvec_index* idx, const float* query, uint32_t limit, uint64_t* out_rows, float* out_scores,
+                    uint32_t* out_count);
+
+/* ---- flat matrix file: MemoryOptimizer::save_to_mmap / load_from_mmap (codegraph-vector/src/memory.rs:241-374):
+ * [u64 vector_count][u64 dimension][count*dimension f32 row-major].  load appends the file's rows (no ids) and
+ * rejects a wrong dimension or file size exactly like the reference loader. */
+int cgvec_save_flat(const cgvec_index* idx, const char* path);
+int cgvec_load_flat(cgvec_index* idx, const char* path, uint64_t* out_rows_loaded);
+
 /* ---- host-side helpers (pure CPU, no device needed; used by the shim and by the gloo tests) ---- */
 
 /* Row range [begin, end) owned by `rank` of `world` for a contiguous split of n rows. */

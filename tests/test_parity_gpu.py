@@ -354,3 +354,67 @@ def test_every_launch_geometry_is_exact(cg, oracle, tile, stages):
         wi, ws = oracle.parallel_top_k_search(qs[0], rows, 5)
         assert r[0].tolist() == wi.tolist() and s[0].tobytes() == ws.tobytes()
     ix.close()
+
+
+def test_flat_matrix_file_round_trip(cg, oracle, tmp_path):
+    """memory.rs:241-374: [u64 n][u64 d][n*d f32].  A file written the reference's way loads; a saved index reads back
+    the reference's way; wrong dimension / truncated files are rejected like load_from_mmap does."""
+    rng = np.random.default_rng(77)
+    rows = rng.standard_normal((3000, 96)).astype(np.float32)
+    ref_file = tmp_path / "ref.bin"
+    with open(ref_file, "wb") as f:
+        f.write(np.array([3000, 96], np.uint64).tobytes()); f.write(rows.tobytes())
+    ix = cg.Index(96)
+    assert ix.load_flat(str(ref_file)) == 3000 and len(ix) == 3000
+    q = rng.standard_normal(96).astype(np.float32)
+    wi, ws = oracle.parallel_top_k_search(q, rows, 10)
+    r, s, _ = ix.search(q, 10)
+    assert r[0].tolist() == wi.tolist() and s[0].tobytes() == ws.tobytes()
+    out_file = tmp_path / "out.bin"
+    ix.save_flat(str(out_file))
+    assert open(out_file, "rb").read() == open(ref_file, "rb").read()
+    bad = cg.Index(64)
+    with pytest.raises(cg.CgvecError) as e:
+        bad.load_flat(str(ref_file))
+    assert e.value.code == cg.ERR_BAD_DIM
+    trunc = tmp_path / "trunc.bin"
+    trunc.write_bytes(open(ref_file, "rb").read()[:-4])
+    with pytest.raises(cg.CgvecError):
+        ix.load_flat(str(trunc))
+    ix.close(); bad.close()
+
+
+def test_int8_quantised_scan_matches_search_optimized(cg, oracle):
+    """SURVEY §8f-3.  Codes == quantize_batch (optimization.rs:212-224,268-274) byte for byte; search_optimized
+    (:63-150) scores bit-identical; indices identical wherever scores are distinct (the reference's order among
+    exactly equal int8 scores depends on its insertion history); and the reference's own property
+    (model_optimization_tests.rs:383-424): >= 80 % position-wise agreement with search_baseline."""
+    vecs = oracle.generate_optimization_vectors(1000, 128, 11223)
+    ix = cg.Index(128)
+    ix.add(vecs)
+    ix.quantize_i8()
+    want_codes = oracle.quantize_batch_u8(vecs)
+    assert ix.codes_i8(0, 1000).tobytes() == want_codes.tobytes()
+    q = vecs[0]
+    got_i, got_s = ix.search_optimized(q, 10)
+    want_i, want_s = oracle.search_optimized_i8(q, want_codes, 10)
+    assert got_s.tobytes() == want_s.tobytes()
+    if len(set(want_s.tolist())) == len(want_s):
+        assert got_i.tolist() == want_i.tolist()
+    base, _ = oracle.search_baseline(q, vecs, 10)
+    assert float(np.mean(got_i == base)) >= 0.8
+    # larger, ragged dimension, values outside [-1, 1] (clamped), NaN element (-> code 128), zero row (skipped)
+    rng = np.random.default_rng(5)
+    rows = (rng.standard_normal((20_000, 100)) * 0.7).astype(np.float32)
+    rows[17, 3] = np.nan; rows[99] = 0.0
+    ix2 = cg.Index(100); ix2.add(rows); ix2.quantize_i8()
+    codes = oracle.quantize_batch_u8(rows)
+    assert ix2.codes_i8(0, 20_000).tobytes() == codes.tobytes()
+    for limit in (1, 7, 50):
+        q = rng.standard_normal(100).astype(np.float32) * 0.5
+        gi, gs = ix2.search_optimized(q, limit)
+        wi, ws = oracle.search_optimized_i8(q, codes, limit)
+        assert gs.tobytes() == ws.tobytes()
+        assert sorted(gi.tolist()) == sorted(wi.tolist()) or len(set(ws.tolist())) < len(ws)
+    assert len(ix2.search_optimized(np.zeros(100, np.float32), 5)[0]) == 0          # zero query -> empty (:113-115)
+    ix.close(); ix2.close()

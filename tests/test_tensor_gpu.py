@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(cg, oracle, n, d, nq, k, seed, expect_no_fallback=True, rows=None, queries=None):
+def _run(cg, oracle, n, d, nq, k, seed, expect_no_fallback=True, rows=None, queries=None, opts=None):
     rng = np.random.default_rng(seed)
     if rows is None:
         rows = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
@@ -17,6 +17,8 @@ def _run(cg, oracle, n, d, nq, k, seed, expect_no_fallback=True, rows=None, quer
     ix = cg.Index(d, cg.F16)
     try:
         ix.add(rows)
+        for key, val in (opts or {}).items():
+            ix.set_option(key, val)
         r, s, c = ix.search(queries, k, cg.COSINE, path=cg.PATH_TENSOR)
         st = ix.stats()
         assert st.tc_batches >= 1
@@ -89,3 +91,20 @@ def test_auto_path_picks_tensor_for_large_f16_batches(cg, oracle):
         ix.search(qs, 10, path=cg.PATH_TENSOR)
     assert e.value.code == cg.ERR_UNSUPPORTED
     ix.close()
+
+
+@pytest.mark.parametrize("d,nq,k", [(128, 16, 10), (128, 64, 10), (768, 256, 100), (1024, 64, 100), (1000, 200, 10), (256, 250, 5)])
+def test_paired_cta_kernel_matches_oracle(cg, oracle, d, nq, k):
+    """K2b (cta_group::2): CTA pairs, M = 256, query block streamed — up to 256 queries in one HBM pass."""
+    st = _run(cg, oracle, 70_000, d, nq, k, seed=d + nq, opts={"tc_kernel": 2})
+    assert st.tc_batches == 1
+
+
+def test_paired_cta_kernel_row_tails_and_small_indexes(cg, oracle):
+    for n in (5, 255, 256, 257, 8_192 + 300):
+        _run(cg, oracle, n, 128, 32, 10, seed=n, opts={"tc_kernel": 2})
+
+
+def test_auto_uses_pairs_for_batches_beyond_the_resident_limit(cg, oracle):
+    st = _run(cg, oracle, 50_000, 768, 256, 10, seed=5)          # 256 queries at d=768 cannot stay resident
+    assert st.tc_batches == 1
