@@ -1127,11 +1127,10 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         rc = ensure(&c->h_counts, &c->hcnt_cap, nq, true); if (rc) return finish(rc);
     }
     if (o.formula == CGVEC_FORMULA_SIMD) {
-        rc = run_queries(ix, c, c->d_q, qstride, nq, k, o.metric, o.path, st, c->d_rows, c->d_scores, c->d_counts);
+        // Results are decoded straight into the pinned host mirrors (device-accessible under UVA): ~130 bytes of
+        // posted PCIe writes from the last kernel replace three device-to-host copies per call.
+        rc = run_queries(ix, c, c->d_q, qstride, nq, k, o.metric, o.path, st, c->h_rows, c->h_scores, c->h_counts);
         if (rc) return finish(rc);
-        CUDA_TRY(cudaMemcpyAsync(c->h_rows, c->d_rows, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(c->h_scores, c->d_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     } else {
         if (ix->world > 1 || ix->row_offset != 0) return finish(fail(CGVEC_ERR_UNSUPPORTED, "non-SIMD formulas are not available on sharded indexes yet"));
