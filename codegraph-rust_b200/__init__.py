@@ -37,7 +37,7 @@ EXPORTS = [
     "cgvec_add_f16", "cgvec_normalize_rows", "cgvec_fill_synthetic", "cgvec_len", "cgvec_dim", "cgvec_search",
     "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
     "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
-    "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_last_error", "cgvec_version",
+    "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_get_trace", "cgvec_last_error", "cgvec_version",
 ]
 
 
@@ -112,6 +112,7 @@ def load_library(build: bool = True):
     L.cgvec_normalize_scores.argtypes = [vp, C.c_size_t]; L.cgvec_normalize_scores.restype = None
     L.cgvec_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.cgvec_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.cgvec_get_trace.argtypes = [vp, vp, C.c_uint32, u32p]
     L.cgvec_last_error.restype = C.c_char_p
     L.cgvec_version.restype = C.c_char_p
     _lib = L
@@ -304,6 +305,12 @@ class Index:
         s = Stats()
         _check(load_library().cgvec_get_stats(self._h, C.byref(s)))
         return s
+
+    def trace(self, max_entries: int = 16384) -> np.ndarray:
+        """-> int64[n, 3]: kind (1 scan, 2 merge, 3 exchange), start ns, end ns of every launch traced so far."""
+        out = np.zeros((max_entries, 3), np.uint64); n = C.c_uint32()
+        _check(load_library().cgvec_get_trace(self._h, _ptr(out), max_entries, C.byref(n)))
+        return out[: n.value].astype(np.int64)
 
     def set_option(self, key: str, value: int):
         _check(load_library().cgvec_set_option(self._h, key.encode(), value))

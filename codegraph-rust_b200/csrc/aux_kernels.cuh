@@ -161,9 +161,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
                                                                     uint32_t sort_n, uint64_t* __restrict__ out, int ascending,
                                                                     uint64_t* __restrict__ out_rows,
                                                                     float* __restrict__ out_scores,
-                                                                    uint32_t* __restrict__ out_counts, int sorted_in) {
+                                                                    uint32_t* __restrict__ out_counts, int sorted_in,
+                                                                    uint64_t* trace) {
     extern __shared__ __align__(16) uint64_t s_merge_keys[];
     uint64_t* s_keys = s_merge_keys;
+    if (threadIdx.x == 0) trace_begin(trace);
     // Let a programmatically-dependent successor (the next query's scan, which does not read our output) start now.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t q = blockIdx.y, n_out = gridDim.x;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
             if (threadIdx.x == 0) out_counts[q] = s_cnt;
         }
     }
+    if (threadIdx.x == 0) trace_end(trace);
 }
 
 // cosine DISTANCE of the first `limit` rows (gpu.rs:297-322 compute_distances_cpu), one octet lane 0 per row.

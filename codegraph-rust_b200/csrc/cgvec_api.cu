@@ -148,6 +148,10 @@ struct Index {
     // knobs (cgvec_set_option)
     int opt_tile_rows = 0, opt_stages = 0, opt_sync = 0, opt_l2_hint = 0, opt_grid = 0, opt_timing = 0, opt_max_nq = kScanMaxQ;
     int opt_pdl = 1;
+    // launch timeline (option "trace"): [kind, start ns, end ns] per traced launch, device-resident until read back
+    uint64_t* d_trace = nullptr;
+    std::vector<uint32_t> trace_kinds;      // 1 = scan, 2 = merge, 3 = exchange
+    static constexpr uint32_t kTraceCap = 16384;
     int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 0, opt_tc_first = 0, opt_tc_kernel = 0, opt_tc_debug = 0, opt_tc2_max_n = kTc2MaxN;
     int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0;
     std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
@@ -244,6 +248,12 @@ int grow(Index* ix, uint64_t need, bool exact = false) {
     ix->d_norms = nnorms;
     ix->cap = newcap;
     return CGVEC_OK;
+}
+
+uint64_t* trace_slot(Index* ix, uint32_t kind) {
+    if (!ix->d_trace || ix->trace_kinds.size() >= Index::kTraceCap) return nullptr;
+    ix->trace_kinds.push_back(kind);
+    return ix->d_trace + 2 * (ix->trace_kinds.size() - 1);
 }
 
 ScanParams map_params(const Index* ix) {
@@ -399,7 +409,7 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         if (tournament) sort_n = per_cta * list_len;            // staging area size (keys) ahead of the level-2 lists
         merge_topk_kernel<<<grid, kMergeThreads, smem, st>>>(cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
                                                             last ? d_rows : nullptr, last ? d_scores : nullptr,
-                                                            last ? d_counts : nullptr, sorted_in);
+                                                            last ? d_counts : nullptr, sorted_in, trace_slot(ix, 2));
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
         if (last) break;
@@ -472,6 +482,7 @@ int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t
     p.rows = ix->d_rows; p.norms = ix->d_norms; p.queries = d_q; p.partials = partials;
     p.n_rows = ix->n; p.d = ix->dim; p.ld = ix->ld; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
     p.stages = g.stages; p.active_groups = g.groups; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
+    p.trace = trace_slot(ix, 1);
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ix->opt_timing) {
@@ -511,6 +522,7 @@ int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t 
             xp.rank = (uint32_t)ix->rank; xp.world = (uint32_t)ix->world; xp.seq = ++ix->xseq;
             for (int r = 0; r < ix->world; ++r) xp.peer[r] = ix->xpeer[r];
             xp.out_rows = d_rows; xp.out_scores = d_scores; xp.out_counts = d_counts;
+            xp.trace = trace_slot(ix, 3);
             const size_t smem = ((size_t)lists * k + 9 * k) * 8;
             xchg_merge_kernel<<<nq, kXchgThreads, smem, st>>>(xp);
             ix->launches++;
@@ -547,14 +559,14 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // 2-D fp16 tensor map, K (inner) x rows, 128-byte swizzle, box = 64 halves x box_rows, OOB reads as zero.
 int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows,
-                  int l2promo = 1) {
+                  int l2promo = 1, bool f32 = false) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {inner, rows};
     cuuint64_t gstr[1] = {row_stride_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)kTcKBlock, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? kTcKBlock / 2 : kTcKBlock), box_rows};   // 128 bytes of K either way
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B,
                     l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -565,12 +577,13 @@ int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t r
 constexpr uint32_t kTcCap = 8192;     // candidate slots per query between selects (one CTA sorts them in smem)
 
 bool tensor_path_applicable(const Index* ix, int metric, uint32_t nq) {
-    return ix->dtype == CGVEC_F16 && metric == CGVEC_COSINE && nq >= 1 && ix->n >= 1;
+    return metric == CGVEC_COSINE && nq >= 1 && ix->n >= 1;      // f16 rows -> kind::f16, f32 rows -> kind::tf32
 }
 
 // Largest MMA N (multiple of 16) whose resident query block leaves >= 3 row stages in shared memory (tc_scan_kernel).
 uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
-    const uint32_t nkb = (ix->dim + kTcKBlock - 1) / kTcKBlock;
+    const uint32_t kbe = ix->dtype == CGVEC_F32 ? kTcKBlock / 2 : kTcKBlock;
+    const uint32_t nkb = (ix->dim + kbe - 1) / kbe;
     uint32_t limit = (uint32_t)ix->opt_tc_max_n;
     if (limit > kTcMaxN) limit = kTcMaxN;
     for (uint32_t N = limit & ~15u; N >= 16; N -= 16) {
@@ -614,7 +627,9 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     const uint32_t n_max = pairs ? kTc2MaxN : tc_max_n(ix, &stages);
     if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
     const uint32_t N = (nq + 15) & ~15u;
-    const uint32_t nkb = (ix->dim + kTcKBlock - 1) / kTcKBlock, dpad = nkb * kTcKBlock;
+    const bool f32 = ix->dtype == CGVEC_F32;
+    const uint32_t kbe = f32 ? kTcKBlock / 2 : kTcKBlock;            // elements per 128-byte K-block
+    const uint32_t nkb = (ix->dim + kbe - 1) / kbe, dpad = nkb * kbe;
     if (pairs) {
         stages = tc2_stages(ix, N);
         if (stages < 2) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the paired tensor kernel at N = %u", N);
@@ -630,7 +645,7 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     if (kp < k) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u is too large for the tensor path", k);
 
     int rc;
-    rc = ensure(&c->d_B, &c->B_cap, (size_t)N * dpad); if (rc) return rc;
+    rc = ensure(&c->d_B, &c->B_cap, (size_t)N * dpad * (f32 ? 2 : 1)); if (rc) return rc;      // capacity counted in halves
     rc = ensure(&c->d_tc_f, &c->tcf_cap, (size_t)3 * kTc2MaxN); if (rc) return rc;
     rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)2 * kTc2MaxN + 4); if (rc) return rc;
     rc = ensure(&c->d_cand, &c->cand_cap, (size_t)kTc2MaxN * kTcCap); if (rc) return rc;
@@ -639,13 +654,14 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     float *d_thr = c->d_tc_f, *d_na = c->d_tc_f + kTc2MaxN, *d_rho = c->d_tc_f + 2 * kTc2MaxN;
     uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTc2MaxN, *d_overflow = c->d_tc_u + 2 * kTc2MaxN;
 
-    tc_prep_queries_kernel<<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, c->d_B, d_na, d_rho, d_thr, d_cnt, d_overflow);
+    if (f32) tc_prep_queries_kernel<float><<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, reinterpret_cast<float*>(c->d_B), d_na, d_rho, d_thr, d_cnt, d_overflow);
+    else tc_prep_queries_kernel<__half><<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, c->d_B, d_na, d_rho, d_thr, d_cnt, d_overflow);
     ix->launches++;
     CUDA_TRY(cudaGetLastError());
 
     CUtensorMap tmA, tmB;
-    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * 2, kTcTileRows, ix->opt_tc_l2promo); if (rc) return rc;
-    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * 2, pairs ? N / 2 : N); if (rc) return rc;
+    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * ix->esize, kTcTileRows, ix->opt_tc_l2promo, f32); if (rc) return rc;
+    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * ix->esize, pairs ? N / 2 : N, 1, f32); if (rc) return rc;
 
     TcParams p{};
     ScanParams map = map_params(ix);
@@ -654,6 +670,7 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     p.tmem_cols = next_pow2(2 * N) < 32 ? 32 : next_pow2(2 * N);
     p.prefetch_dist = (uint32_t)ix->opt_tc_prefetch;
     p.debug = (uint32_t)ix->opt_tc_debug;
+    p.tf32 = f32 ? 1u : 0u;
     p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
     const uint32_t smem = (pairs ? tc2_smem_layout(N, stages).total : tc_smem_layout(N, nkb, stages).total) + 1024;
 
@@ -697,9 +714,12 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     // exact re-score of the survivors, sort, proof
     {
         const uint32_t total = nq * kp;
-        tc_rescore_kernel<__half><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride,
-                                                                          d_na, ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE,
-                                                                          ix->row_offset, c->d_exact);
+        if (f32)
+            tc_rescore_kernel<float><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
+                                                                             ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, ix->row_offset, c->d_exact);
+        else
+            tc_rescore_kernel<__half><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
+                                                                              ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, ix->row_offset, c->d_exact);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -707,7 +727,9 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     // sorted exact keys [nq][kp] (needed by the proof) ...
     uint64_t* sorted = c->d_part[1];
     rc = merge_lists(ix, c, c->d_exact, nq, 1, kp, 0, sorted, nullptr, nullptr, nullptr, st, kp, kp, kp, /*sorted_in=*/0); if (rc) return rc;
-    const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f;
+    // tensor accumulation + oracle accumulation; with TF32 the ROWS are truncated as well (<= 2^-10 relative each,
+    // the query's share is measured in rho): |err| <= (rho_q + 2^-10 + rho_q 2^-10) |q||r|.
+    const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f + (f32 ? 1.0e-3f : 0.0f);
     tc_verify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c->d_cand, kTcCap, d_cnt, kp, sorted, want ? want : 1, d_na, d_rho, acc_bound, METRIC_COSINE, nq,
                                                       d_proven, d_overflow);
     ix->launches++;
@@ -743,10 +765,11 @@ int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uin
                 uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
     bool tensor = false;
     if (path == CGVEC_PATH_TENSOR) {
-        if (!tensor_path_applicable(ix, metric, nq)) return fail(CGVEC_ERR_UNSUPPORTED, "the tensor-core path serves f16 storage with the cosine metric");
+        if (!tensor_path_applicable(ix, metric, nq)) return fail(CGVEC_ERR_UNSUPPORTED, "the tensor-core path serves the cosine metric");
         tensor = true;
     } else if (path == CGVEC_PATH_AUTO) {
-        tensor = tensor_path_applicable(ix, metric, nq) && nq >= (uint32_t)ix->opt_tc_min_nq && ix->n >= 4 * kTcCap && k <= kTcCap / 16;
+        const uint32_t min_nq = ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq;
+        tensor = tensor_path_applicable(ix, metric, nq) && nq >= min_nq && ix->n >= 4 * kTcCap && k <= kTcCap / 16;
     }
     uint32_t n_max = tensor ? tc_batch_limit(ix, nq) : 0;
     if (tensor && n_max == 0) {
@@ -927,6 +950,7 @@ CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
     cudaFree(ix->d_norms);
     cudaFree(ix->d_codes);
     cudaFree(ix->d_inorms);
+    cudaFree(ix->d_trace);
     if (ix->main_stream) cudaStreamDestroy(ix->main_stream);
     delete ix;
     return CGVEC_OK;
@@ -1657,6 +1681,20 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; }
     else if (k == "max_batch") ix->opt_max_nq = (int)value;
     else if (k == "pdl") ix->opt_pdl = (int)value;
+    else if (k == "trace") {
+        cudaSetDevice(ix->device);
+        if (value && !ix->d_trace) {
+            if (cudaMalloc(reinterpret_cast<void**>(&ix->d_trace), Index::kTraceCap * 16) != cudaSuccess) { ix->d_trace = nullptr; return fail(CGVEC_ERR_OOM, "trace buffer"); }
+        }
+        if (ix->d_trace) {
+            cudaDeviceSynchronize();
+            std::vector<uint64_t> init(Index::kTraceCap * 2);
+            for (uint32_t i = 0; i < Index::kTraceCap; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+            cudaMemcpy(ix->d_trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+            ix->trace_kinds.clear();
+        }
+        if (!value && ix->d_trace) { cudaFree(ix->d_trace); ix->d_trace = nullptr; }
+    }
     else if (k == "p2p") ix->opt_p2p = (int)value;
     else if (k == "tc_min_batch") ix->opt_tc_min_nq = (int)value;
     else if (k == "tc_stages") ix->opt_tc_stages = (int)value;
@@ -1670,6 +1708,23 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "tc_debug") ix->opt_tc_debug = (int)value;
     else if (k == "tc2_max_n") ix->opt_tc2_max_n = (int)value;
     else return fail(CGVEC_ERR_BAD_ARG, "unknown option '%s'", key);
+    return CGVEC_OK;
+}
+
+// Launch timeline recorded since option "trace" was set: out[3*i] = kind (1 scan, 2 merge, 3 exchange), start ns, end ns.
+CGVEC_EXPORT int cgvec_get_trace(const cgvec_index* cix, uint64_t* out, uint32_t max_entries, uint32_t* out_n) {
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix || !out_n) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
+    *out_n = 0;
+    if (!ix->d_trace) return CGVEC_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    uint32_t n = (uint32_t)ix->trace_kinds.size();
+    if (n > max_entries) n = max_entries;
+    std::vector<uint64_t> raw((size_t)n * 2);
+    if (n) CUDA_TRY(cudaMemcpy(raw.data(), ix->d_trace, raw.size() * 8, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n && out; ++i) { out[3 * i] = ix->trace_kinds[i]; out[3 * i + 1] = raw[2 * i]; out[3 * i + 2] = raw[2 * i + 1]; }
+    *out_n = n;
     return CGVEC_OK;
 }
 

@@ -71,6 +71,16 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// Optional launch timeline (cgvec_set_option "trace"): every CTA folds the global nanosecond timer into a
+// [first start, last end] pair of its launch; used by tools/trace_steps.py to see gaps between kernels.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(uint64_t* slot) { if (slot) atomicMin(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)global_ns()); }
+__device__ __forceinline__ void trace_end(uint64_t* slot) { if (slot) atomicMax(reinterpret_cast<unsigned long long*>(slot) + 1, (unsigned long long)global_ns()); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -34,6 +34,7 @@ struct XchgParams {
     uint64_t* out_rows;
     float* out_scores;
     uint32_t* out_counts;
+    uint64_t* trace;
 };
 
 __device__ __forceinline__ uint32_t* xchg_flags(uint8_t* base) { return reinterpret_cast<uint32_t*>(base); }
@@ -52,6 +53,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(kXchgThreads) xchg_merge_kernel(const XchgParams p) {
     extern __shared__ __align__(16) uint64_t s_x[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) trace_begin(p.trace);
     const uint32_t q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t parity = p.seq & 1u;
     // ---- 0. this shard's best k of query q
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_merge_kernel(const XchgPara
         __syncthreads();
         if (tid == 0) p.out_counts[q] = s_cnt;
     }
+    if (tid == 0) trace_end(p.trace);
 }
 
 }  // namespace cgv

@@ -55,6 +55,7 @@ struct ScanParams {
     // global row = ((local / blk_rows) * n_shards + shard_id) * blk_rows + local % blk_rows + row_offset
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
+    uint64_t* trace;           // optional [start, end] slot of this launch (see common.cuh trace_begin)
 };
 
 __host__ __device__ inline uint32_t scan_row_words(uint32_t ld, uint32_t esize) {
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
     const uint64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid == 0) {
+        trace_begin(p.trace);
         for (uint32_t s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], warps_per_stage);
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
             uint64_t* out = p.partials + ((size_t)j * gridDim.x + blockIdx.x) * p.k;
             for (uint32_t i = ctid; i < p.k; i += nct) out[i] = (i < cnt) ? s_cand[(size_t)j * p.cand_cap + i] : 0ull;
         }
+        if (ctid == 0) trace_end(p.trace);
     }
 }
 

@@ -52,6 +52,7 @@ struct TcParams {
     uint32_t metric;            // METRIC_COSINE or METRIC_DOT
     uint32_t tmem_cols;         // power of two >= 2*N, >= 32
     uint32_t prefetch_dist;     // K-blocks of L2 prefetch issued ahead of the demand loads (0 = off)
+    uint32_t tf32;              // 0: f16 rows/queries (kind::f16, 64 elements per 128-byte K-block); 1: f32 rows/queries as TF32 (kind::tf32, 32)
     uint32_t debug;             // bit 0: skip the MMAs, bit 1: skip the epilogue body (bandwidth triage only; results invalid)
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
@@ -112,6 +113,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ inline uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// kind::tf32: A = B = TF32 (format 2 at bits [7,10) and [10,13)); f32 operands in shared memory, low mantissa bits ignored
+__host__ __device__ inline uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -241,12 +264,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_prefetch_desc(&tmB);
             const uint64_t pol = l2_policy_evict_first();
             mbar_arrive_expect_tx(b_bar, p.nkb * p.N * 128);
-            for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.N * 128, &tmB, kb * kTcKBlock, 0, b_bar);
+            const int kbe = p.tf32 ? kTcKBlock / 2 : kTcKBlock;       // elements per 128-byte K-block
+            for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.N * 128, &tmB, kb * kbe, 0, b_bar);
             const uint64_t total_it = my_tiles * p.nkb;
             auto prefetch_block = [&](uint64_t j) {
                 const uint64_t t = j / p.nkb;
                 const uint32_t kb = (uint32_t)(j - t * p.nkb);
-                tma_prefetch_2d(&tmA, kb * kTcKBlock, (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows));
+                tma_prefetch_2d(&tmA, kb * kbe, (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows));
             };
             for (uint64_t j = 0; j < p.prefetch_dist && j < total_it; ++j) prefetch_block(j);
             uint64_t it = 0;
@@ -257,14 +281,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t s = it % p.stages;
                     if (it >= p.stages) mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
-                    tma_load_2d_hint(sA + (size_t)s * kTcStageBytes, &tmA, kb * kTcKBlock, row0, &full_bar[s], pol);
+                    tma_load_2d_hint(sA + (size_t)s * kTcStageBytes, &tmA, kb * kbe, row0, &full_bar[s], pol);
                 }
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTcTileRows, p.N);
+            const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kTcTileRows, p.N) : umma_idesc_f16(kTcTileRows, p.N);
             mbar_wait(b_bar, 0);
             tc_fence_after();
             uint64_t it = 0;
@@ -281,8 +305,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_addr = smem_u32(sB + (size_t)kb * p.N * 128);
                     if (!(p.debug & 1u)) {
 #pragma unroll
-                        for (uint32_t k = 0; k < kTcKBlock / 16; ++k)
-                            umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                        for (uint32_t k = 0; k < kTcKBlock / 16; ++k) {      // 4 MMAs per 128-byte K-block: K = 16 halves or 8 tf32 each
+                            if (p.tf32) umma_tf32_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                            else umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[s]);                          // stage free once these MMAs retire
                 }
@@ -293,7 +319,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
         // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); they split the query columns.
         const uint32_t q4 = warp & 3;
-        const uint32_t col_split = ((p.N / 16 + 1) / 2) * 16;
+        const uint32_t col_split = (p.debug & 4u) ? p.N : ((p.N / 16 + 1) / 2) * 16;      // debug bit 2: first warp set takes every column
         const uint32_t col_begin = warp < 4 ? 0u : col_split, col_end = warp < 4 ? col_split : p.N;
         for (uint64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = t & 1;
@@ -435,15 +461,16 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (it >= p.stages) mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
                     uint8_t* st = smem + (size_t)s * lay.stage_bytes;
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * lay.stage_bytes);     // both CTAs' bytes land on the leader
-                    tma_load_2d_2sm(st, &tmA, kb * kTcKBlock, row0, &full_bar[s], pol);
-                    tma_load_2d_2sm(st + kTcStageBytes, &tmB, kb * kTcKBlock, (int)(rank * half_n), &full_bar[s], pol_keep);
+                    const int kbe = p.tf32 ? kTcKBlock / 2 : kTcKBlock;
+                    tma_load_2d_2sm(st, &tmA, kb * kbe, row0, &full_bar[s], pol);
+                    tma_load_2d_2sm(st + kTcStageBytes, &tmB, kb * kbe, (int)(rank * half_n), &full_bar[s], pol_keep);
                 }
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kPairRows, p.N);
+            const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kPairRows, p.N) : umma_idesc_f16(kPairRows, p.N);
             uint64_t it = 0;
             for (uint64_t t = 0; t < my_tiles; ++t) {
                 const uint32_t buf = t & 1;
@@ -457,8 +484,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t a_addr = smem_u32(smem + (size_t)s * lay.stage_bytes);
                     const uint32_t b_addr = a_addr + kTcStageBytes;
 #pragma unroll
-                    for (uint32_t k = 0; k < kTcKBlock / 16; ++k)
-                        umma_f16_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    for (uint32_t k = 0; k < kTcKBlock / 16; ++k) {
+                        if (p.tf32) umma_tf32_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                        else umma_f16_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    }
                     umma_commit_2sm(&empty_bar[s]);
                 }
                 umma_commit_2sm(&tfull_bar[buf]);
@@ -467,7 +496,7 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp < 4 || warp >= 8) {
         // ===================== epilogue (both CTAs; each owns its 128 rows of the pair tile) =====================
         const uint32_t q4 = warp & 3;
-        const uint32_t col_split = ((p.N / 16 + 1) / 2) * 16;
+        const uint32_t col_split = (p.debug & 4u) ? p.N : ((p.N / 16 + 1) / 2) * 16;      // debug bit 2: first warp set takes every column
         const uint32_t col_begin = warp < 4 ? 0u : col_split, col_end = warp < 4 ? col_split : p.N;
         for (uint64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = t & 1;
@@ -519,10 +548,11 @@ __global__ void __launch_bounds__(1024) tc_select_kernel(uint64_t* __restrict__ 
     }
 }
 
-// ---- query preparation: f32 queries -> fp16 B operand (zero padded), exact |q|^2, rounding-error ratio -------
-// One octet per query.  rho[q] >= ||q - fp16(q)|| / ||q||  (inflated 1%) feeds the host-side error bound.
+// ---- query preparation: f32 queries -> B operand (fp16, or f32 read as TF32; zero padded), exact |q|^2, and the
+// operand-rounding ratio rho[q] >= ||q - rounded(q)|| / ||q|| (inflated 1%) that feeds the error bound.  One octet per query.
+template <typename TB>
 __global__ void tc_prep_queries_kernel(const float* __restrict__ q, uint32_t qstride, uint32_t nq, uint32_t N, uint32_t d, uint32_t dpad,
-                                       __half* __restrict__ B, float* __restrict__ na, float* __restrict__ rho, float* __restrict__ thr,
+                                       TB* __restrict__ B, float* __restrict__ na, float* __restrict__ rho, float* __restrict__ thr,
                                        uint32_t* __restrict__ cand_count, uint32_t* __restrict__ overflow) {
     const uint32_t octet = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int L = threadIdx.x & 7;
@@ -533,9 +563,16 @@ __global__ void tc_prep_queries_kernel(const float* __restrict__ q, uint32_t qst
     float e2 = 0.0f, s2 = 0.0f;
     for (uint32_t i = L; i < dpad; i += 8) {
         float x = (real && i < d) ? v[i] : 0.0f;
-        __half h = __float2half_rn(x);
-        if (octet < N) B[(size_t)qi * dpad + i] = h;
-        float e = x - __half2float(h);
+        float xr;
+        if (sizeof(TB) == 2) {
+            __half h = __float2half_rn(x);
+            if (octet < N) reinterpret_cast<__half*>(B)[(size_t)qi * dpad + i] = h;
+            xr = __half2float(h);
+        } else {
+            if (octet < N) reinterpret_cast<float*>(B)[(size_t)qi * dpad + i] = x;
+            xr = __uint_as_float(__float_as_uint(x) & 0xffffe000u);      // what kind::tf32 sees: low 13 mantissa bits dropped
+        }
+        float e = x - xr;
         e2 += e * e;
         s2 += x * x;
     }

@@ -193,6 +193,9 @@ typedef struct {
 } cgvec_stats;
 int cgvec_get_stats(const cgvec_index* idx, cgvec_stats* out);
 int cgvec_set_option(cgvec_index* idx, const char* key, int64_t value);   /* tuning knobs, see DESIGN.md */
+/* Device-side launch timeline (after cgvec_set_option(idx, "trace", 1)): out[3*i] = kind (1 scan, 2 merge, 3 exchange),
+ * out[3*i+1] = first CTA start, out[3*i+2] = last CTA end, both in %globaltimer nanoseconds. */
+int cgvec_get_trace(const cgvec_index* idx, uint64_t* out, uint32_t max_entries, uint32_t* out_n);
 
 const char* cgvec_last_error(void);
 const char* cgvec_version(void);

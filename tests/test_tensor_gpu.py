@@ -7,14 +7,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(cg, oracle, n, d, nq, k, seed, expect_no_fallback=True, rows=None, queries=None, opts=None):
+def _run(cg, oracle, n, d, nq, k, seed, expect_no_fallback=True, rows=None, queries=None, opts=None, f32=False):
     rng = np.random.default_rng(seed)
     if rows is None:
         rows = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
     if queries is None:
         queries = rng.standard_normal((nq, d)).astype(np.float32)
-    ref_rows = rows.astype(np.float16).astype(np.float32)
-    ix = cg.Index(d, cg.F16)
+    ref_rows = rows if f32 else rows.astype(np.float16).astype(np.float32)
+    ix = cg.Index(d, cg.F32 if f32 else cg.F16)
     try:
         ix.add(rows)
         for key, val in (opts or {}).items():
@@ -84,11 +84,11 @@ def test_auto_path_picks_tensor_for_large_f16_batches(cg, oracle):
     assert ix.stats().tc_batches == 1
     assert r1.tolist() == r[:2].tolist() and s1.tobytes() == s[:2].tobytes()
     ix.close()
-    # f32 storage never takes the f16 tensor path
-    ix = cg.Index(128, cg.F32)
+    # the tensor path serves cosine only
+    ix = cg.Index(128, cg.F16)
     ix.add(rows)
     with pytest.raises(cg.CgvecError) as e:
-        ix.search(qs, 10, path=cg.PATH_TENSOR)
+        ix.search(qs, 10, cg.L2, path=cg.PATH_TENSOR)
     assert e.value.code == cg.ERR_UNSUPPORTED
     ix.close()
 
@@ -108,3 +108,10 @@ def test_paired_cta_kernel_row_tails_and_small_indexes(cg, oracle):
 def test_auto_uses_pairs_for_batches_beyond_the_resident_limit(cg, oracle):
     st = _run(cg, oracle, 50_000, 768, 256, 10, seed=5)          # 256 queries at d=768 cannot stay resident
     assert st.tc_batches == 1
+
+
+@pytest.mark.parametrize("d,nq,k,kernel", [(128, 64, 10, 1), (384, 64, 10, 1), (384, 256, 10, 2), (768, 32, 100, 1), (100, 48, 10, 2)])
+def test_tf32_tensor_path_for_f32_storage(cg, oracle, d, nq, k, kernel):
+    """f32 rows go through kind::tf32 (both operands lose 13 mantissa bits inside the tensor core); the exact re-score
+    and the wider error bound still deliver bit-exact results (BASELINE config 5's storage type)."""
+    _run(cg, oracle, 60_000, d, nq, k, seed=d * 3 + nq, f32=True, opts={"tc_kernel": kernel})

@@ -15,11 +15,12 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--path", default="tensor")
+    ap.add_argument("--dtype", default="f16")
     ap.add_argument("--opt", action="append", default=[])
     args = ap.parse_args()
     cg = ge.load_package()
     import torch
-    ix = cg.Index(args.dim, cg.F16)
+    ix = cg.Index(args.dim, cg.F16 if args.dtype == "f16" else cg.F32)
     ix.reserve(args.rows)
     ix.fill_synthetic(args.rows, 0xC0DE6A9F, True)
     for o in args.opt:
@@ -46,9 +47,9 @@ def main():
     wall = time.perf_counter() - t0
     s = ix.stats()
     ms = e0.elapsed_time(e1) / args.iters
-    alg = args.rows * args.dim * 2
+    alg = args.rows * args.dim * (2 if args.dtype == "f16" else 4)
     passes = -(-args.nq // 128) if args.path != "exact" else args.nq
-    print(json.dumps({"rows": args.rows, "dim": args.dim, "nq": args.nq, "k": args.k, "path": args.path, "ms_per_batch": round(ms, 3),
+    print(json.dumps({"rows": args.rows, "dim": args.dim, "nq": args.nq, "k": args.k, "path": args.path, "dtype": args.dtype, "ms_per_batch": round(ms, 3),
                       "wall_ms_per_batch": round(wall / args.iters * 1e3, 3), "qps": round(args.nq / ms * 1e3, 1),
                       "GBps_per_pass": round(alg * passes / ms / 1e6, 1), "scan_ms_events": round(s.scan_ms_total / max(s.scans_timed, 1), 3),
                       "launches_per_batch": (s.kernel_launches - l0) / args.iters, "tc_batches": s.tc_batches, "tc_fallbacks": s.tc_fallbacks,
