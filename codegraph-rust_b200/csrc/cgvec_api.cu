@@ -422,11 +422,17 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
     return CGVEC_OK;
 }
 
+int ensure_parts(SearchCtx* c, size_t need_part);
+
 // Exchange step of a sharded index: this rank's best-k keys [nq][k] -> one NCCL all-gather -> every rank merges
 // the `world` lists and decodes.  The single collective of the path.
 int exchange_and_decode(Index* ix, SearchCtx* c, uint64_t* local_keys, uint32_t nq, uint32_t k, int ascending, cudaStream_t st,
                         uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
     size_t per_rank = (size_t)nq * k;
+    {   // the gathered [rank][query][k] layout is re-packed to [query][rank][k] in the merge scratch
+        int rc = ensure_parts(c, per_rank * (size_t)ix->world);
+        if (rc) return rc;
+    }
     {
         std::lock_guard<std::mutex> lk(ix->comm_mu);
         NCCL_TRY(nccl_api().AllGather(local_keys, c->d_gather, per_rank, kNcclUint64, ix->comm, st));

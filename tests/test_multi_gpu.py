@@ -18,7 +18,7 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, uid_q, rows, qs, k, metric_name, out):
+def _worker(rank, world, uid_q, rows, qs, k, metric_name, out, dtype_name="f32", path_name="auto"):
     sys.path.insert(0, ROOT)
     import __graft_entry__ as ge
     cg = ge.load_package()
@@ -31,11 +31,14 @@ def _worker(rank, world, uid_q, rows, qs, k, metric_name, out):
     else:
         uid = uid_q.get(timeout=120)
     b, e = cg.shard_range(len(rows), world, rank)
-    ix = cg.Index(rows.shape[1], cg.F32, device=rank, rank=rank, world=world, nccl_unique_id=uid, row_offset=b)
+    dt = cg.F32 if dtype_name == "f32" else cg.F16
+    ix = cg.Index(rows.shape[1], dt, device=rank, rank=rank, world=world, nccl_unique_id=uid, row_offset=b)
     ix.add(rows[b:e])
     metric = {"cosine": cg.COSINE, "l2": cg.L2}[metric_name]
-    r, s, c = ix.search(qs, k, metric)
-    out[rank] = (r.tolist(), s.tobytes(), c.tolist())
+    path = {"auto": cg.PATH_AUTO, "tensor": cg.PATH_TENSOR}[path_name]
+    r, s, c = ix.search(qs, k, metric, path=path)
+    st = ix.stats()
+    out[rank] = (r.tolist(), s.tobytes(), c.tolist(), int(st.tc_batches), int(st.tc_fallbacks))
     ix.close()
 
 
@@ -62,7 +65,7 @@ def test_sharded_search_equals_oracle(oracle, metric_name):
         for qi in range(3):
             wi, ws = oracle.parallel_top_k_search(qs[qi], rows, k, metric=om)
             for r in range(world):
-                gr, gs, gc = out[r]
+                gr, gs, gc = out[r][:3]
                 assert gc[qi] == k
                 assert gr[qi] == wi.tolist()
                 assert np.frombuffer(gs, np.float32).reshape(3, k)[qi].tobytes() == ws.tobytes()
@@ -109,3 +112,33 @@ def test_single_process_multi_device_index(cg, oracle, dtype_name):
     b = cg.Index(d, dt); b.fill_synthetic(5000, 77, True)
     assert a.get_rows(0, 5000).tobytes() == b.get_rows(0, 5000).tobytes()
     a.close(); b.close()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("dtype_name,k", [("f16", 100), ("f16", 10), ("f32", 100)])
+def test_sharded_tensor_path_equals_oracle(oracle, dtype_name, k):
+    """BASELINE config 4's shape in small: row-sharded f16 (and f32/TF32) index, batch-64 queries, tensor-core scan per
+    shard, exact per-shard top-k exchanged with ONE NCCL all-gather, every rank returns the oracle's answer."""
+    import torch.multiprocessing as mp
+    world = min(_ngpus(), 4)
+    rng = np.random.default_rng(53)
+    n, d, nq = 120_000, 256, 64
+    rows = (rng.standard_normal((n, d)) / 16).astype(np.float32)
+    qs = rng.standard_normal((nq, d)).astype(np.float32)
+    ref = rows if dtype_name == "f32" else rows.astype(np.float16).astype(np.float32)
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict(); uid_q = ctx.Queue()
+        procs = [ctx.Process(target=_worker, args=(r, world, uid_q, rows, qs, k, "cosine", out, dtype_name, "tensor")) for r in range(world)]
+        [p.start() for p in procs]
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0
+        for r in range(world):
+            gr, gs, gc, batches, fallbacks = out[r]
+            assert batches >= 1 and fallbacks == 0
+            got_s = np.frombuffer(gs, np.float32).reshape(nq, k)
+            for qi in range(0, nq, 7):
+                wi, ws = oracle.parallel_top_k_search(qs[qi], ref, k)
+                assert gr[qi] == wi.tolist()
+                assert got_s[qi].tobytes() == ws.tobytes()
