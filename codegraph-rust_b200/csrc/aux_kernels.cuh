@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
     if (threadIdx.x == 0) trace_begin(trace);
     // Let a programmatically-dependent successor (the next query's scan, which does not read our output) start now.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // No-op unless this kernel was itself launched programmatically (PDL chain mode 2): then the producer of `in` may
+    // still be running and must have completed (memory visible) before the first read below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t q = blockIdx.y, n_out = gridDim.x;
     const uint32_t first = blockIdx.x * lists_per_cta;
     const uint32_t lists = min(lists_per_cta, n_lists - first);

@@ -147,7 +147,7 @@ struct Index {
 
     // knobs (cgvec_set_option)
     int opt_tile_rows = 0, opt_stages = 0, opt_sync = 0, opt_l2_hint = 0, opt_grid = 0, opt_timing = 0, opt_max_nq = kScanMaxQ;
-    int opt_pdl = 1;
+    int opt_pdl = 2;            // 0: plain launches, 1: merge releases the next scan early, 2: full programmatic chain
     // launch timeline (option "trace"): [kind, start ns, end ns] per traced launch, device-resident until read back
     uint64_t* d_trace = nullptr;
     std::vector<uint32_t> trace_kinds;      // 1 = scan, 2 = merge, 3 = exchange
@@ -407,9 +407,17 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         const bool tournament = sorted_in && k <= kTournamentMaxK && per_cta <= 256;
         const size_t smem = tournament ? ((size_t)per_cta * list_len + 8 * k) * 8 : (size_t)sort_n * 8;
         if (tournament) sort_n = per_cta * list_len;            // staging area size (keys) ahead of the level-2 lists
-        merge_topk_kernel<<<grid, kMergeThreads, smem, st>>>(cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
-                                                            last ? d_rows : nullptr, last ? d_scores : nullptr,
-                                                            last ? d_counts : nullptr, sorted_in, trace_slot(ix, 2));
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = grid; cfg.blockDim = dim3(kMergeThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = ix->opt_pdl >= 2 ? 1 : 0;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_topk_kernel, cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
+                                        last ? d_rows : (uint64_t*)nullptr, last ? d_scores : (float*)nullptr, last ? d_counts : (uint32_t*)nullptr,
+                                        sorted_in, trace_slot(ix, 2)));
+        }
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
         if (last) break;
@@ -489,6 +497,7 @@ int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t
     p.n_rows = ix->n; p.d = ix->dim; p.ld = ix->ld; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
     p.stages = g.stages; p.active_groups = g.groups; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
     p.trace = trace_slot(ix, 1);
+    p.early_trigger = (ix->opt_pdl >= 2 && g.grid >= (uint32_t)ix->sm_count) ? 1u : 0u;   // only with every SM occupied
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ix->opt_timing) {
@@ -530,9 +539,16 @@ int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t 
             xp.out_rows = d_rows; xp.out_scores = d_scores; xp.out_counts = d_counts;
             xp.trace = trace_slot(ix, 3);
             const size_t smem = ((size_t)lists * k + 9 * k) * 8;
-            xchg_merge_kernel<<<nq, kXchgThreads, smem, st>>>(xp);
+            {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(nq); cfg.blockDim = dim3(kXchgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = ix->opt_pdl >= 2 ? 1 : 0;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, xchg_merge_kernel, xp));
+            }
             ix->launches++;
-            CUDA_TRY(cudaGetLastError());
             return CGVEC_OK;
         }
         uint64_t* local_keys = nullptr;

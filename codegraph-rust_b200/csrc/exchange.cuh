@@ -53,6 +53,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(kXchgThreads) xchg_merge_kernel(const XchgParams p) {
     extern __shared__ __align__(16) uint64_t s_x[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // PDL chain mode 2: the scan that wrote `partials` has completed
     if (threadIdx.x == 0) trace_begin(p.trace);
     const uint32_t q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t parity = p.seq & 1u;

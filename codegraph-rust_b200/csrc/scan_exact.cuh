@@ -56,6 +56,7 @@ struct ScanParams {
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
     uint64_t* trace;           // optional [start, end] slot of this launch (see common.cuh trace_begin)
+    uint32_t early_trigger;    // PDL chain mode 2: release dependents at once, order our partial-list WRITE after the predecessor
 };
 
 __host__ __device__ inline uint32_t scan_row_words(uint32_t ld, uint32_t esize) {
@@ -207,6 +208,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
     const uint64_t num_tiles = (p.n_rows + p.tile_rows - 1) / p.tile_rows;
     const uint64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
+    // PDL chain (mode 2).  Every kernel of the per-query chain scan -> merge/exchange -> scan -> ... releases its
+    // dependents immediately and executes griddepcontrol.wait before its first access that could conflict with its
+    // predecessor: the merge before READING our partial lists, we before WRITING them (double buffered: the previous
+    // reader of this buffer is the merge two kernels back).  By induction along the chain, passing our wait implies every
+    // older kernel has completed, so the scanning itself may overlap the previous query's tail and merge.
+    if (p.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         trace_begin(p.trace);
         for (uint32_t s = 0; s < p.stages; ++s) {
@@ -315,6 +322,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
         while (next_boundary < my_tiles) { sync_and_maybe_compact(false); next_boundary += epoch; }
         sync_and_maybe_compact(true);
         // sorted best-k keys of this CTA (0-padded)
+        if (p.early_trigger) asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
             const uint32_t cnt = s_count[j];

@@ -418,3 +418,33 @@ def test_int8_quantised_scan_matches_search_optimized(cg, oracle):
         assert sorted(gi.tolist()) == sorted(wi.tolist()) or len(set(ws.tolist())) < len(ws)
     assert len(ix2.search_optimized(np.zeros(100, np.float32), 5)[0]) == 0          # zero query -> empty (:113-115)
     ix.close(); ix2.close()
+
+
+@pytest.mark.parametrize("pdl", [0, 1, 2])
+def test_back_to_back_device_resident_searches(cg, oracle, pdl):
+    """The throughput path: hundreds of batch-1 searches enqueued on one stream with device-resident I/O and no host
+    sync in between.  pdl=1 overlaps each merge with the next scan; pdl=2 chains every kernel programmatically
+    (early release + griddepcontrol.wait before the first conflicting access).  Every result must still be exact."""
+    import torch
+    rng = np.random.default_rng(60 + pdl)
+    n, d, k, steps = 60_000, 256, 10, 300
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    qs = rng.standard_normal((steps, d)).astype(np.float32)
+    ix = cg.Index(d)
+    ix.add(rows)
+    ix.set_option("pdl", pdl)
+    dq = torch.from_numpy(qs).cuda()
+    o_r = torch.zeros((steps, k), dtype=torch.int64, device="cuda")
+    o_s = torch.zeros((steps, k), dtype=torch.float32, device="cuda")
+    o_c = torch.zeros((steps,), dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    for rep in range(2):
+        for i in range(steps):
+            ix.search_device(dq[i].data_ptr(), 1, k, o_r[i].data_ptr(), o_s[i].data_ptr(), o_c[i].data_ptr(), cg.COSINE, st.cuda_stream)
+    torch.cuda.synchronize()
+    got_r, got_s = o_r.cpu().numpy(), o_s.cpu().numpy()
+    assert int(o_c.min()) == k
+    for i in range(0, steps, 3):
+        wi, ws = oracle.parallel_top_k_search(qs[i], rows, k)
+        assert got_r[i].tolist() == wi.tolist() and got_s[i].tobytes() == ws.tobytes(), i
+    ix.close()
