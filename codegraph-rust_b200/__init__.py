@@ -36,7 +36,7 @@ EXPORTS = [
     "cgvec_create", "cgvec_create_rank", "cgvec_nccl_unique_id", "cgvec_destroy", "cgvec_reserve", "cgvec_add",
     "cgvec_add_f16", "cgvec_normalize_rows", "cgvec_fill_synthetic", "cgvec_len", "cgvec_dim", "cgvec_search",
     "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
-    "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
+    "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_multi_locate", "cgvec_multi_local_count", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
     "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_get_trace", "cgvec_last_error", "cgvec_version",
 ]
 
@@ -106,6 +106,8 @@ def load_library(build: bool = True):
     L.cgvec_save_flat.argtypes = [vp, C.c_char_p]
     L.cgvec_load_flat.argtypes = [vp, C.c_char_p, u64p]
     L.cgvec_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+    L.cgvec_multi_locate.argtypes = [C.c_uint32, C.c_uint64, u32p, u64p]
+    L.cgvec_multi_local_count.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]; L.cgvec_multi_local_count.restype = C.c_uint64
     L.cgvec_merge_topk_host.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, u32p]
     L.cgvec_prefetch_k_basic.argtypes = [C.c_uint64]; L.cgvec_prefetch_k_basic.restype = C.c_uint64
     L.cgvec_prefetch_k_filtered.argtypes = [C.c_uint64]; L.cgvec_prefetch_k_filtered.restype = C.c_uint64
@@ -328,6 +330,16 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return int(b.value), int(e.value)
 
 
+def multi_locate(n_devices: int, global_row: int) -> Tuple[int, int]:
+    s, l = C.c_uint32(), C.c_uint64()
+    _check(load_library().cgvec_multi_locate(n_devices, global_row, C.byref(s), C.byref(l)))
+    return int(s.value), int(l.value)
+
+
+def multi_local_count(n_devices: int, shard: int, n_rows: int) -> int:
+    return int(load_library().cgvec_multi_local_count(n_devices, shard, n_rows))
+
+
 def merge_topk_host(rows, scores, counts, k: int, ascending: bool = False):
     r = np.ascontiguousarray(rows, np.uint64); s = np.ascontiguousarray(scores, np.float32)
     c = np.ascontiguousarray(counts, np.uint32)
@@ -452,6 +464,21 @@ class SemanticSearch:
         order = order[:limit]
         norm = normalize_scores(raw[order])                                        # search.rs:138
         return [SearchResult(ids[j], float(s)) for j, s in zip(order, norm)]
+
+
+def resolve_symbol(index: "Index", target_embedding, candidate_rows, threshold: float = 0.75):
+    """AI symbol resolver arg-max (codegraph-mcp/src/indexer.rs:2827-2843, cosine :2965-2979): among the candidate rows
+    that survived the caller's trigram prefilter, the FIRST row with the highest cosine (search.rs:519-533 arithmetic,
+    computed on the device) strictly above `threshold`; None if none.  -> (row, similarity) | None"""
+    cand = np.ascontiguousarray(candidate_rows, np.uint64)
+    if cand.size == 0:
+        return None
+    sims = index.rescore(target_embedding, cand, COSINE, FORMULA_SEQ)
+    best = None
+    for r, s in zip(cand.tolist(), sims.tolist()):
+        if s > threshold and (best is None or s > best[1]):      # indexer.rs:2832-2840: strict >, first best wins
+            best = (int(r), float(s))
+    return best
 
 
 class GpuAcceleration:

@@ -1605,6 +1605,23 @@ CGVEC_EXPORT int cgvec_shard_range(uint64_t n, int world, int rank, uint64_t* be
     return CGVEC_OK;
 }
 
+// Placement rule of the single-process multi-device index (multi_device.inl): rows are dealt in kMultiBlk-row blocks
+// round-robin.  Exposed so that host code (and the CPU tests) can reason about where a global row lives.
+CGVEC_EXPORT int cgvec_multi_locate(uint32_t n_devices, uint64_t global_row, uint32_t* out_shard, uint64_t* out_local_row) {
+    if (n_devices == 0) return fail(CGVEC_ERR_BAD_ARG, "n_devices must be >= 1");
+    const uint64_t b = global_row / kMultiBlk;
+    if (out_shard) *out_shard = (uint32_t)(b % n_devices);
+    if (out_local_row) *out_local_row = (b / n_devices) * kMultiBlk + global_row % kMultiBlk;
+    return CGVEC_OK;
+}
+CGVEC_EXPORT uint64_t cgvec_multi_local_count(uint32_t n_devices, uint32_t shard, uint64_t n_rows) {
+    if (n_devices == 0 || shard >= n_devices) return 0;
+    const uint64_t full = n_rows / kMultiBlk, rem = n_rows % kMultiBlk;
+    uint64_t c = (full / n_devices) * kMultiBlk + ((full % n_devices) > shard ? kMultiBlk : 0);
+    if (full % n_devices == shard) c += rem;
+    return c;
+}
+
 CGVEC_EXPORT int cgvec_merge_topk_host(const uint64_t* rows, const float* scores, const uint32_t* counts, uint32_t parts, uint32_t k,
                                        int ascending, uint64_t* out_rows, float* out_scores, uint32_t* out_count) {
     if ((!rows || !scores || !counts) && parts && k) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");

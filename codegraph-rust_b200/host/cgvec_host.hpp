@@ -212,6 +212,21 @@ private:
     size_t ef_;
 };
 
+// AI symbol resolver arg-max (codegraph-mcp/src/indexer.rs:2827-2843; cosine :2965-2979 == search.rs:519-533): among the
+// candidates the caller's trigram prefilter kept, the first one with the highest cosine strictly above the threshold.
+inline std::optional<std::pair<NodeId, float>> resolve_symbol(const B200VectorStore& store, const std::vector<float>& target_embedding,
+                                                              const std::vector<NodeId>& candidates, float threshold = 0.75f) {
+    if (candidates.empty()) return std::nullopt;
+    std::vector<uint64_t> rows(candidates.size());
+    for (size_t i = 0; i < candidates.size(); ++i) check(cgvec_row_of_id(store.handle(), candidates[i].bytes.data(), &rows[i]));
+    std::vector<float> sims(rows.size());
+    check(cgvec_rescore(store.handle(), target_embedding.data(), rows.data(), (uint32_t)rows.size(), CGVEC_COSINE, CGVEC_FORMULA_SEQ, sims.data()));
+    std::optional<std::pair<NodeId, float>> best;
+    for (size_t i = 0; i < rows.size(); ++i)
+        if (sims[i] > threshold && (!best || sims[i] > best->second)) best = std::make_pair(candidates[i], sims[i]);
+    return best;
+}
+
 struct SearchResult {
     NodeId node_id;
     float score;

@@ -167,6 +167,10 @@ int cgvec_load_flat(cgvec_index* idx, const char* path, uint64_t* out_rows_loade
 
 /* Row range [begin, end) owned by `rank` of `world` for a contiguous split of n rows. */
 int cgvec_shard_range(uint64_t n, int world, int rank, uint64_t* begin, uint64_t* end);
+/* Placement of a global row in a single-process multi-device index (1024-row blocks dealt round-robin), and the number
+ * of rows device `shard` holds when the index has n_rows. */
+int cgvec_multi_locate(uint32_t n_devices, uint64_t global_row, uint32_t* out_shard, uint64_t* out_local_row);
+uint64_t cgvec_multi_local_count(uint32_t n_devices, uint32_t shard, uint64_t n_rows);
 /* Merge `parts` partial top-k lists (each k entries: global row + score, best first, counts[p] valid)
  * into the global top-k under the result contract.  ascending != 0 for L2 / BASELINE. */
 int cgvec_merge_topk_host(const uint64_t* rows, const float* scores, const uint32_t* counts, uint32_t parts,

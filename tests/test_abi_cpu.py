@@ -140,3 +140,21 @@ def test_synth_mirror_properties():
     assert abs(float(raw.mean())) < 0.01 and 0.5 < float(raw.std()) < 0.65
     assert synth.synth_raw(1, [5], 8).tobytes() == synth.synth_raw(1, [5], 8).tobytes()
     assert synth.synth_raw(1, [5], 8).tobytes() != synth.synth_raw(2, [5], 8).tobytes()
+
+
+def test_multi_device_placement_is_a_bijection(cg):
+    """Single-process multi-device index: global rows <-> (device, local row) through 1024-row blocks dealt round-robin."""
+    for G in (1, 2, 3, 8):
+        for n in (0, 1, 1023, 1024, 1025, 5000, 8 * 1024 * 3 + 17):
+            counts = [cg.multi_local_count(G, s, n) for s in range(G)]
+            assert sum(counts) == n
+            assert max(counts) - min(counts) <= 1024
+            seen = set()
+            for g in list(range(min(n, 3000))) + list(range(max(0, n - 3000), n)):
+                s, l = cg.multi_locate(G, g)
+                assert 0 <= s < G and l < counts[s]
+                seen.add((s, l))
+                if g + 1 < n:                       # order inside a device follows global order (tie rule survives)
+                    s2, l2 = cg.multi_locate(G, g + 1)
+                    assert (s2 != s) or (l2 == l + 1)
+            assert len(seen) == len(set(list(range(min(n, 3000))) + list(range(max(0, n - 3000), n))))

@@ -448,3 +448,19 @@ def test_back_to_back_device_resident_searches(cg, oracle, pdl):
         wi, ws = oracle.parallel_top_k_search(qs[i], rows, k)
         assert got_r[i].tolist() == wi.tolist() and got_s[i].tobytes() == ws.tobytes(), i
     ix.close()
+
+
+def test_symbol_resolver_argmax(cg, oracle):
+    """indexer.rs:2827-2843 — best candidate strictly above 0.75 by the search.rs:519-533 cosine."""
+    rng = np.random.default_rng(88)
+    embs = rng.standard_normal((400, 384)).astype(np.float32)
+    target = embs[123] + 0.3 * rng.standard_normal(384).astype(np.float32)
+    ix = cg.Index(384)
+    ix.add(embs)
+    cands = np.array([5, 123, 77, 300, 123], np.uint64)
+    got = cg.resolve_symbol(ix, target, cands)
+    sims = [oracle.cosine_similarity_seq(target, embs[int(c)]) for c in cands]
+    assert got is not None and got[0] == 123 and np.float32(got[1]) == np.float32(sims[1]) and got[1] > 0.75
+    assert cg.resolve_symbol(ix, target, np.array([5, 77, 300], np.uint64)) is None       # nothing above the threshold
+    assert cg.resolve_symbol(ix, target, np.array([], np.uint64)) is None
+    ix.close()
