@@ -226,6 +226,22 @@ class Index:
             return rows, scores, counts, ids[:, :k]
         return rows, scores, counts
 
+    def make_search_buffers(self, nq: int, k: int):
+        """Preallocated host outputs + cached C pointers for search_into (the low-overhead calling convention a server
+        loop uses: no per-call allocation or marshalling beyond the query pointer)."""
+        rows = np.full((nq, k), 2**64 - 1, np.uint64); scores = np.zeros((nq, k), np.float32); counts = np.zeros(nq, np.uint32)
+        opts = SearchOpts(C.sizeof(SearchOpts), COSINE, FORMULA_SIMD, PATH_AUTO, None, 0)
+        return {"rows": rows, "scores": scores, "counts": counts, "opts": opts, "nq": nq, "k": k,
+                "p_rows": _ptr(rows), "p_scores": _ptr(scores), "p_counts": _ptr(counts), "p_opts": C.byref(opts)}
+
+    def search_into(self, queries: np.ndarray, bufs, metric: int = COSINE):
+        """cgvec_search_ex with host buffers; `queries` must be C-contiguous float32 [nq, dim]; results land in bufs."""
+        bufs["opts"].metric = metric
+        rc = load_library().cgvec_search_ex(self._h, queries.ctypes.data_as(C.c_void_p), bufs["nq"], bufs["k"], bufs["p_opts"],
+                                            bufs["p_rows"], None, bufs["p_scores"], bufs["p_counts"])
+        if rc:
+            _check(rc)
+
     def search_device(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int,
                       metric: int = COSINE, stream: int = 0, path: int = PATH_AUTO):
         """Device-resident I/O (raw device pointers); asynchronous on `stream`."""

@@ -36,7 +36,7 @@ def _newer(target: str, sources) -> bool:
 
 
 def lib_sources():
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".inl"))]
     srcs.append(os.path.join(ROOT, "include", "cgvec.h"))
     return srcs
 

@@ -1,7 +1,9 @@
 // cgvec_api.cu — the C ABI of libcgvec_b200.so (include/cgvec.h): index lifecycle, the write side
-// (store_embeddings), the search orchestration (scan -> per-CTA partials -> merge -> [NCCL all-gather ->
-// merge] -> decode) and the host-side helpers.  No CPU scoring path exists in this file: without an
-// sm_100 device every compute entry point returns CGVEC_ERR_NO_DEVICE.
+// (store_embeddings), the exported search / re-score / int8 / file entry points and the host-side helpers.
+// The orchestration lives in three includes: host_scan.inl (exact-order path: plan, launch, merge, exchange),
+// host_tensor.inl (tcgen05 path: row ranges, thresholds, exact re-score + proof) and multi_device.inl
+// (one process driving several GPUs).  No CPU scoring path exists: without an sm_100 device every compute
+// entry point returns CGVEC_ERR_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -278,610 +280,8 @@ int launch_norms(Index* ix, uint64_t first, uint64_t count, cudaStream_t st) {
     return CGVEC_OK;
 }
 
-// ---- scan planning / launch ---------------------------------------------------------------------
-int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
-    g->row_words = scan_row_words(ix->ld, ix->esize);
-    const uint32_t try_tiles[4] = {16, 32, 8, 4};
-    uint32_t best_bytes = 0;
-    for (int t = 0; t < 4; ++t) {
-        uint32_t tile = ix->opt_tile_rows ? (uint32_t)ix->opt_tile_rows : try_tiles[t];
-        if (tile != 4 && tile != 8 && tile != 16 && tile != 32) return fail(CGVEC_ERR_BAD_ARG, "tile_rows must be 4, 8, 16 or 32");
-        const uint32_t gmax = kScanConsumerWarps / (tile / 4);
-        uint32_t max_stages = ix->opt_stages ? (uint32_t)ix->opt_stages : 8;
-        for (uint32_t s = max_stages; s >= 2; --s) {
-            // A stage must always be drained by the same warp group, otherwise a group would wait on a phase of the
-            // stage's mbarrier without having observed the previous one (parity aliasing): active groups divide stages.
-            uint32_t groups = 1;
-            for (uint32_t a = gmax; a >= 1; --a) if (s % a == 0) { groups = a; break; }
-            if (ix->opt_stages == 0 && groups < gmax && groups * 2 <= gmax && s > 2) continue;   // prefer well-populated groupings
-            uint32_t sync = ix->opt_sync ? (uint32_t)ix->opt_sync : 8;
-            sync = ((sync + groups - 1) / groups) * groups;
-            uint32_t cand = next_pow2(k + sync * tile);
-            if (cand < 64) cand = 64;
-            ScanSmemLayout L = scan_smem_layout(g->row_words, tile, s, ix->dim, nq, cand);
-            if (L.total > kSmemBudget) continue;
-            uint32_t bytes = s * tile * g->row_words * 4;
-            if (bytes > best_bytes + best_bytes / 8) {          // keep the first (preferred) tile unless another buffers >12% more
-                best_bytes = bytes;
-                g->tile_rows = tile; g->stages = s; g->groups = groups; g->sync_interval = sync; g->cand_cap = cand; g->smem = L.total;
-            }
-            break;
-        }
-        if (ix->opt_tile_rows) break;
-    }
-    if (!best_bytes) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u (k=%u, nq=%u) does not fit the scan kernel's shared memory", ix->dim, k, nq);
-    uint64_t tiles = (ix->n + g->tile_rows - 1) / g->tile_rows;
-    uint32_t grid = ix->opt_grid ? (uint32_t)ix->opt_grid : (uint32_t)ix->sm_count;
-    g->grid = (uint32_t)(tiles < grid ? tiles : grid);
-    if (g->grid == 0) g->grid = 1;
-    return CGVEC_OK;
-}
-
-// cudaFuncSetAttribute is per device: remember which (function, device) pairs have been raised already.
-template <typename F>
-int ensure_smem_attr(F func, uint32_t bytes) {
-    static std::mutex mu;
-    static std::vector<std::pair<const void*, int>> done;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const void* key = reinterpret_cast<const void*>(func);
-    std::lock_guard<std::mutex> lk(mu);
-    for (auto& d : done) if (d.first == key && d.second == dev) return CGVEC_OK;
-    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return fail(CGVEC_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
-    done.emplace_back(key, dev);
-    return CGVEC_OK;
-}
-
-template <typename T, int METRIC, int NQ>
-int launch_scan_t(const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
-    int arc = ensure_smem_attr(scan_exact_kernel<T, METRIC, NQ>, kSmemBudget);
-    if (arc) return arc;
-    // Programmatic dependent launch: the kernel ahead of us in the stream is normally the previous query's merge,
-    // whose output we do not read (partials are double buffered), so our CTAs may start as soon as it has started.
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(g.grid);
-    cfg.blockDim = dim3(kScanThreads);
-    cfg.dynamicSmemBytes = g.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g.pdl ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, scan_exact_kernel<T, METRIC, NQ>, p));
-    return CGVEC_OK;
-}
-template <typename T, int METRIC>
-int launch_scan_q(uint32_t nq, const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
-    switch (nq) {
-        case 1: return launch_scan_t<T, METRIC, 1>(p, g, st);
-        case 2: return launch_scan_t<T, METRIC, 2>(p, g, st);
-        case 4: return launch_scan_t<T, METRIC, 4>(p, g, st);
-    }
-    return fail(CGVEC_ERR_BAD_ARG, "internal: scan batch %u", nq);
-}
-template <typename T>
-int launch_scan_m(int metric, uint32_t nq, const ScanParams& p, const ScanGeom& g, cudaStream_t st) {
-    switch (metric) {
-        case CGVEC_COSINE: return launch_scan_q<T, METRIC_COSINE>(nq, p, g, st);
-        case CGVEC_DOT: return launch_scan_q<T, METRIC_DOT>(nq, p, g, st);
-        case CGVEC_L2: return launch_scan_q<T, METRIC_L2>(nq, p, g, st);
-    }
-    return fail(CGVEC_ERR_BAD_ARG, "unknown metric %d", metric);
-}
-
-// Merge `lists` key lists per query (element (q, l, i) at in[q*q_stride + l*l_stride + i]) down to one list of k.
-// The final level decodes into d_rows/d_scores/d_counts when given, and/or writes keys to `final_keys`.
-int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32_t lists, uint32_t k, int ascending,
-                uint64_t* final_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, cudaStream_t st,
-                size_t q_stride, size_t l_stride, uint32_t list_len = 0, int sorted_in = 1) {
-    if (list_len == 0) list_len = k;
-    {
-        int arc = ensure_smem_attr(merge_topk_kernel, kMergeMaxKeys * 8);
-        if (arc) return arc;
-    }
-    // the kernel reads list l of query q at in + (q*n_lists + l)*k: repack when the caller's layout differs
-    const uint64_t* cur = in;
-    uint32_t cur_lists = lists;
-    int pp = 0;
-    if (!(q_stride == (size_t)lists * list_len && l_stride == list_len)) {
-        // gathered layout [list][nq][len] -> [nq][list][len] with strided 2D copies (device to device)
-        uint64_t* dst = c->d_part[0];
-        for (uint32_t q = 0; q < nq; ++q)
-            CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)q * lists * list_len, (size_t)list_len * 8, in + q * q_stride, l_stride * 8,
-                                       (size_t)list_len * 8, lists, cudaMemcpyDeviceToDevice, st));
-        cur = dst;
-        pp = 1;
-    }
-    while (true) {
-        uint32_t per_cta_max = (kMergeMaxKeys - 8 * kTournamentMaxK) / list_len < 2 ? 2 : (kMergeMaxKeys - 8 * kTournamentMaxK) / list_len;
-        if (per_cta_max > 256) per_cta_max = 256;
-        uint32_t per_cta = cur_lists < per_cta_max ? cur_lists : per_cta_max;
-        uint32_t n_out = (cur_lists + per_cta - 1) / per_cta;
-        uint32_t sort_n = next_pow2(per_cta * list_len);
-        if (sort_n < 2) sort_n = 2;
-        const bool last = (n_out == 1);
-        uint64_t* out = last ? final_keys : c->d_part[pp];
-        dim3 grid(n_out, nq);
-        const bool tournament = sorted_in && k <= kTournamentMaxK && per_cta <= 256;
-        const size_t smem = tournament ? ((size_t)per_cta * list_len + 8 * k) * 8 : (size_t)sort_n * 8;
-        if (tournament) sort_n = per_cta * list_len;            // staging area size (keys) ahead of the level-2 lists
-        {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = grid; cfg.blockDim = dim3(kMergeThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = ix->opt_pdl >= 2 ? 1 : 0;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_topk_kernel, cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
-                                        last ? d_rows : (uint64_t*)nullptr, last ? d_scores : (float*)nullptr, last ? d_counts : (uint32_t*)nullptr,
-                                        sorted_in, trace_slot(ix, 2)));
-        }
-        ix->launches++;
-        CUDA_TRY(cudaGetLastError());
-        if (last) break;
-        cur = out;
-        cur_lists = n_out;
-        list_len = k;
-        sorted_in = 1;
-        pp ^= 1;
-    }
-    return CGVEC_OK;
-}
-
-int ensure_parts(SearchCtx* c, size_t need_part);
-
-// Exchange step of a sharded index: this rank's best-k keys [nq][k] -> one NCCL all-gather -> every rank merges
-// the `world` lists and decodes.  The single collective of the path.
-int exchange_and_decode(Index* ix, SearchCtx* c, uint64_t* local_keys, uint32_t nq, uint32_t k, int ascending, cudaStream_t st,
-                        uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    size_t per_rank = (size_t)nq * k;
-    {   // the gathered [rank][query][k] layout is re-packed to [query][rank][k] in the merge scratch
-        int rc = ensure_parts(c, per_rank * (size_t)ix->world);
-        if (rc) return rc;
-    }
-    {
-        std::lock_guard<std::mutex> lk(ix->comm_mu);
-        NCCL_TRY(nccl_api().AllGather(local_keys, c->d_gather, per_rank, kNcclUint64, ix->comm, st));
-    }
-    return merge_lists(ix, c, c->d_gather, nq, ix->world, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)k, per_rank);
-}
-
-int ensure_gather(Index* ix, SearchCtx* c, uint32_t nq, uint32_t k, uint64_t** local_keys) {
-    size_t per_rank = (size_t)nq * k;
-    size_t cap_g = c->gather_cap;
-    int rc = ensure(&c->d_gather, &cap_g, per_rank * (ix->world + 1));
-    if (rc) return rc;
-    c->gather_cap = cap_g;
-    *local_keys = c->d_gather + per_rank * ix->world;
-    return CGVEC_OK;
-}
-
-int ensure_parts(SearchCtx* c, size_t need_part) {
-    if (need_part > c->part_cap) {
-        size_t cap0 = c->part_cap, cap1 = c->part_cap;
-        int rc = ensure(&c->d_part[0], &cap0, need_part); if (rc) return rc;
-        rc = ensure(&c->d_part[1], &cap1, need_part); if (rc) return rc;
-        c->part_cap = cap0 < cap1 ? cap0 : cap1;
-    }
-    return CGVEC_OK;
-}
-
-// Exact-order scan (K1) of the local shard for `nq` (1, 2 or 4) queries already on the device at `d_q`
-// (stride = dim rounded up to 4 floats).  Leaves this shard's best-k keys in `local_keys` when given, else
-// decodes straight into d_rows/d_scores/d_counts.
-int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
-                uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts,
-                const uint64_t** partials_out = nullptr, uint32_t* lists_out = nullptr) {
-    ScanGeom g;
-    int rc = plan_scan(ix, k, nq, &g);
-    if (rc) return rc;
-    const int ascending = (metric == CGVEC_L2);
-    rc = ensure_parts(c, (size_t)nq * (g.grid > (uint32_t)ix->world ? g.grid : ix->world) * k);
-    if (rc) return rc;
-    {
-        size_t need = (size_t)nq * g.grid * k;
-        if (need > c->scan_cap) {
-            size_t c0 = c->scan_cap, c1 = c->scan_cap;
-            rc = ensure(&c->d_scan[0], &c0, need); if (rc) return rc;
-            rc = ensure(&c->d_scan[1], &c1, need); if (rc) return rc;
-            c->scan_cap = c0 < c1 ? c0 : c1;
-        }
-    }
-    g.pdl = (uint32_t)ix->opt_pdl;
-    uint64_t* partials = c->d_scan[c->scan_flip & 1];
-    c->scan_flip++;
-    ScanParams p = map_params(ix);
-    p.rows = ix->d_rows; p.norms = ix->d_norms; p.queries = d_q; p.partials = partials;
-    p.n_rows = ix->n; p.d = ix->dim; p.ld = ix->ld; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
-    p.stages = g.stages; p.active_groups = g.groups; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
-    p.trace = trace_slot(ix, 1);
-    p.early_trigger = (ix->opt_pdl >= 2 && g.grid >= (uint32_t)ix->sm_count) ? 1u : 0u;   // only with every SM occupied
-
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ix->opt_timing) {
-        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-        CUDA_TRY(cudaEventRecord(e0, st));
-    }
-    rc = (ix->dtype == CGVEC_F32) ? launch_scan_m<float>(metric, nq, p, g, st) : launch_scan_m<__half>(metric, nq, p, g, st);
-    if (rc) return rc;
-    ix->launches++;
-    if (ix->opt_timing) {
-        CUDA_TRY(cudaEventRecord(e1, st));
-        std::lock_guard<std::mutex> lk(ix->ev_mu);
-        ix->timed.emplace_back(e0, e1);
-    }
-    ix->last_geom = g;
-    if (partials_out) { *partials_out = partials; *lists_out = g.grid; return CGVEC_OK; }   // caller fuses merge + exchange
-    return merge_lists(ix, c, partials, nq, g.grid, k, ascending, local_keys, d_rows, d_scores, d_counts, st, (size_t)g.grid * k, k);
-}
-
-int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
-               uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    if (ix->world == 1) return local_exact(ix, c, d_q, nq, k, metric, st, nullptr, d_rows, d_scores, d_counts);
-    if (ix->p2p && ix->opt_p2p && k <= kXchgMaxK && nq <= kXchgMaxQ) {
-        // merge + exchange + merge as one kernel over NVLink peer memory (exchange.cuh)
-        {
-            int arc = ensure_smem_attr(xchg_merge_kernel, 160 * 1024);
-            if (arc) return arc;
-        }
-        const uint64_t* partials = nullptr;
-        uint32_t lists = 0;
-        int rc = local_exact(ix, c, d_q, nq, k, metric, st, nullptr, nullptr, nullptr, nullptr, &partials, &lists);
-        if (rc) return rc;
-        if (lists <= 256) {
-            std::lock_guard<std::mutex> lk(ix->comm_mu);          // same step order on every rank
-            XchgParams xp{};
-            xp.partials = partials; xp.n_lists = lists; xp.k = k; xp.nq = nq; xp.ascending = (metric == CGVEC_L2);
-            xp.rank = (uint32_t)ix->rank; xp.world = (uint32_t)ix->world; xp.seq = ++ix->xseq;
-            for (int r = 0; r < ix->world; ++r) xp.peer[r] = ix->xpeer[r];
-            xp.out_rows = d_rows; xp.out_scores = d_scores; xp.out_counts = d_counts;
-            xp.trace = trace_slot(ix, 3);
-            const size_t smem = ((size_t)lists * k + 9 * k) * 8;
-            {
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3(nq); cfg.blockDim = dim3(kXchgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = ix->opt_pdl >= 2 ? 1 : 0;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, xchg_merge_kernel, xp));
-            }
-            ix->launches++;
-            return CGVEC_OK;
-        }
-        uint64_t* local_keys = nullptr;
-        rc = ensure_gather(ix, c, nq, k, &local_keys);
-        if (rc) return rc;
-        rc = merge_lists(ix, c, partials, nq, lists, k, metric == CGVEC_L2, local_keys, nullptr, nullptr, nullptr, st, (size_t)lists * k, k);
-        if (rc) return rc;
-        return exchange_and_decode(ix, c, local_keys, nq, k, metric == CGVEC_L2, st, d_rows, d_scores, d_counts);
-    }
-    uint64_t* local_keys = nullptr;
-    int rc = ensure_gather(ix, c, nq, k, &local_keys);
-    if (rc) return rc;
-    rc = local_exact(ix, c, d_q, nq, k, metric, st, local_keys, nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    return exchange_and_decode(ix, c, local_keys, nq, k, metric == CGVEC_L2, st, d_rows, d_scores, d_counts);
-}
-
-// ---- tensor-core batched path (K2) -----------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) p = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-// 2-D fp16 tensor map, K (inner) x rows, 128-byte swizzle, box = 64 halves x box_rows, OOB reads as zero.
-int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows,
-                  int l2promo = 1, bool f32 = false) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t gdim[2] = {inner, rows};
-    cuuint64_t gstr[1] = {row_stride_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)(f32 ? kTcKBlock / 2 : kTcKBlock), box_rows};   // 128 bytes of K either way
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B,
-                    l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return CGVEC_OK;
-}
-
-constexpr uint32_t kTcCap = 8192;     // candidate slots per query between selects (one CTA sorts them in smem)
-
-bool tensor_path_applicable(const Index* ix, int metric, uint32_t nq) {
-    return metric == CGVEC_COSINE && nq >= 1 && ix->n >= 1;      // f16 rows -> kind::f16, f32 rows -> kind::tf32
-}
-
-// Largest MMA N (multiple of 16) whose resident query block leaves >= 3 row stages in shared memory (tc_scan_kernel).
-uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
-    const uint32_t kbe = ix->dtype == CGVEC_F32 ? kTcKBlock / 2 : kTcKBlock;
-    const uint32_t nkb = (ix->dim + kbe - 1) / kbe;
-    uint32_t limit = (uint32_t)ix->opt_tc_max_n;
-    if (limit > kTcMaxN) limit = kTcMaxN;
-    for (uint32_t N = limit & ~15u; N >= 16; N -= 16) {
-        for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s) {
-            if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { if (stages_out) *stages_out = s; return N; }
-            if (ix->opt_tc_stages) break;
-        }
-    }
-    return 0;
-}
-// tc2_scan_kernel (CTA pairs) streams the query block: any N <= 256 fits; stages follow from N.
-uint32_t tc2_stages(const Index* ix, uint32_t N) {
-    for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 12; s >= 2; --s)
-        if (tc2_smem_layout(N, s).total + 1024 <= kSmemBudget) return s;
-    return 0;
-}
-// which kernel serves a batch of nq queries, and how many queries one pass may take
-bool tc_use_pairs(const Index* ix, uint32_t nq) {
-    if (ix->opt_tc_kernel == 1) return false;
-    if (ix->opt_tc_kernel == 2) return true;
-    return nq > tc_max_n(ix, nullptr);
-}
-uint32_t tc_batch_limit(const Index* ix, uint32_t nq) {
-    if (tc_use_pairs(ix, nq)) { uint32_t m = (uint32_t)ix->opt_tc2_max_n & ~15u; return m >= 16 && m <= kTc2MaxN ? m : kTc2MaxN; }
-    return tc_max_n(ix, nullptr);
-}
-
-// Tensor-core scan of the local shard for `nq` <= N_max queries (f32, on the device, stride qstride): approximate
-// ordering on tcgen05, exact re-score of the kp survivors per query, proof of exactness; unproven queries are
-// re-run on the exact-order kernel.  Produces this shard's exact best-k keys (`local_keys` [nq][k]) or decoded results.
-int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
-                 uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    {
-        int arc = ensure_smem_attr(tc_scan_kernel, kSmemBudget);
-        if (!arc) arc = ensure_smem_attr(tc2_scan_kernel, kSmemBudget);
-        if (!arc) arc = ensure_smem_attr(tc_select_kernel, kTcCap * 8);
-        if (arc) return arc;
-    }
-    const bool pairs = tc_use_pairs(ix, nq);
-    uint32_t stages = 0;
-    const uint32_t n_max = pairs ? kTc2MaxN : tc_max_n(ix, &stages);
-    if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
-    const uint32_t N = (nq + 15) & ~15u;
-    const bool f32 = ix->dtype == CGVEC_F32;
-    const uint32_t kbe = f32 ? kTcKBlock / 2 : kTcKBlock;            // elements per 128-byte K-block
-    const uint32_t nkb = (ix->dim + kbe - 1) / kbe, dpad = nkb * kbe;
-    if (pairs) {
-        stages = tc2_stages(ix, N);
-        if (stages < 2) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the paired tensor kernel at N = %u", N);
-    } else {   // more stages when the query block is small
-        for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s)
-            if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { stages = s; break; }
-    }
-    const uint32_t tile_rows = pairs ? 2 * kTcTileRows : kTcTileRows;
-    const uint64_t n = ix->n;
-    const uint32_t want = (uint32_t)(k < n ? k : n);
-    uint32_t kp = k + (ix->opt_tc_margin > 0 ? (uint32_t)ix->opt_tc_margin : (k / 2 > 32 ? k / 2 : 32));
-    if (kp > kTcCap / 8) kp = kTcCap / 8;
-    if (kp < k) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u is too large for the tensor path", k);
-
-    int rc;
-    rc = ensure(&c->d_B, &c->B_cap, (size_t)N * dpad * (f32 ? 2 : 1)); if (rc) return rc;      // capacity counted in halves
-    rc = ensure(&c->d_tc_f, &c->tcf_cap, (size_t)3 * kTc2MaxN); if (rc) return rc;
-    rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)2 * kTc2MaxN + 4); if (rc) return rc;
-    rc = ensure(&c->d_cand, &c->cand_cap, (size_t)kTc2MaxN * kTcCap); if (rc) return rc;
-    rc = ensure(&c->d_exact, &c->exact_cap, (size_t)kTc2MaxN * (kTcCap / 8)); if (rc) return rc;
-    rc = ensure(&c->h_proven, &c->hprov_cap, (size_t)kTc2MaxN + 4, true); if (rc) return rc;
-    float *d_thr = c->d_tc_f, *d_na = c->d_tc_f + kTc2MaxN, *d_rho = c->d_tc_f + 2 * kTc2MaxN;
-    uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTc2MaxN, *d_overflow = c->d_tc_u + 2 * kTc2MaxN;
-
-    if (f32) tc_prep_queries_kernel<float><<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, reinterpret_cast<float*>(c->d_B), d_na, d_rho, d_thr, d_cnt, d_overflow);
-    else tc_prep_queries_kernel<__half><<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, c->d_B, d_na, d_rho, d_thr, d_cnt, d_overflow);
-    ix->launches++;
-    CUDA_TRY(cudaGetLastError());
-
-    CUtensorMap tmA, tmB;
-    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * ix->esize, kTcTileRows, ix->opt_tc_l2promo, f32); if (rc) return rc;
-    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * ix->esize, pairs ? N / 2 : N, 1, f32); if (rc) return rc;
-
-    TcParams p{};
-    ScanParams map = map_params(ix);
-    p.n_rows = n; p.norms = ix->d_norms; p.thr = d_thr; p.cand = c->d_cand; p.cand_count = d_cnt; p.overflow = d_overflow;
-    p.cap = kTcCap; p.nq = nq; p.N = N; p.nkb = nkb; p.stages = stages; p.metric = METRIC_COSINE;
-    p.tmem_cols = next_pow2(2 * N) < 32 ? 32 : next_pow2(2 * N);
-    p.prefetch_dist = (uint32_t)ix->opt_tc_prefetch;
-    p.debug = (uint32_t)ix->opt_tc_debug;
-    p.tf32 = f32 ? 1u : 0u;
-    p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
-    const uint32_t smem = (pairs ? tc2_smem_layout(N, stages).total : tc_smem_layout(N, nkb, stages).total) + 1024;
-
-    // geometric row ranges: after T rows the threshold sits at quantile kp/T, so a range of S rows adds about
-    // S*kp/T survivors; ranges are sized to keep each list near `target` entries (small sorts in tc_select_kernel)
-    // and never above cap (overflow -> exact-kernel fallback).
-    uint32_t target = ix->opt_tc_target > 0 ? (uint32_t)ix->opt_tc_target : 1024;
-    if (target < 4 * kp) target = 4 * kp;
-    if (target > kTcCap / 2) target = kTcCap / 2;
-    uint64_t T = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
-    while (T < n) {
-        uint64_t S = (T == 0) ? (ix->opt_tc_first > 0 ? (uint64_t)ix->opt_tc_first : target) : T * (target - kp) / kp;
-        if (T == 0 && S > kTcCap) S = kTcCap;
-        S = (S + tile_rows - 1) / tile_rows * tile_rows;
-        if (S < tile_rows) S = tile_rows;
-        if (T + S > n || (n - T - S) * 8 < S) S = n - T;      // fold a small remainder into this range
-        p.row_begin = T; p.row_end = T + S;
-        uint64_t tiles = (S + tile_rows - 1) / tile_rows;
-        if (pairs) {
-            const uint64_t max_pairs = (uint64_t)ix->sm_count / 2;
-            uint32_t grid = 2 * (uint32_t)(tiles < max_pairs ? tiles : max_pairs);
-            tc2_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
-        } else {
-            uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
-            tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
-        }
-        ix->launches++;
-        CUDA_TRY(cudaGetLastError());
-        tc_select_kernel<<<nq, 1024, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_thr, kTcCap, kp, kTcCap);
-        ix->launches++;
-        CUDA_TRY(cudaGetLastError());
-        T += S;
-    }
-    if (ix->opt_timing) {
-        CUDA_TRY(cudaEventRecord(e1, st));
-        std::lock_guard<std::mutex> lk(ix->ev_mu);
-        ix->timed.emplace_back(e0, e1);
-    }
-    // exact re-score of the survivors, sort, proof
-    {
-        const uint32_t total = nq * kp;
-        if (f32)
-            tc_rescore_kernel<float><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
-                                                                             ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, ix->row_offset, c->d_exact);
-        else
-            tc_rescore_kernel<__half><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
-                                                                              ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, ix->row_offset, c->d_exact);
-        ix->launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
-    rc = ensure_parts(c, (size_t)nq * kp * 2); if (rc) return rc;
-    // sorted exact keys [nq][kp] (needed by the proof) ...
-    uint64_t* sorted = c->d_part[1];
-    rc = merge_lists(ix, c, c->d_exact, nq, 1, kp, 0, sorted, nullptr, nullptr, nullptr, st, kp, kp, kp, /*sorted_in=*/0); if (rc) return rc;
-    // tensor accumulation + oracle accumulation; with TF32 the ROWS are truncated as well (<= 2^-10 relative each,
-    // the query's share is measured in rho): |err| <= (rho_q + 2^-10 + rho_q 2^-10) |q||r|.
-    const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f + (f32 ? 1.0e-3f : 0.0f);
-    tc_verify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c->d_cand, kTcCap, d_cnt, kp, sorted, want ? want : 1, d_na, d_rho, acc_bound, METRIC_COSINE, nq,
-                                                      d_proven, d_overflow);
-    ix->launches++;
-    CUDA_TRY(cudaGetLastError());
-    // ... and this shard's best-k (keys for the exchange, or decoded results when unsharded)
-    rc = merge_lists(ix, c, sorted, nq, 1, k, 0, local_keys, d_rows, d_scores, d_counts, st, kp, kp, kp); if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->h_proven, d_proven, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    ix->tc_batches++;
-    for (uint32_t q = 0; q < nq; ++q) {
-        if (c->h_proven[q]) continue;
-        ix->tc_fallbacks++;                      // could not prove: this query takes the exact-order kernel
-        rc = local_exact(ix, c, d_q + (size_t)q * qstride, 1, k, CGVEC_COSINE, st, local_keys ? local_keys + (size_t)q * k : nullptr,
-                         d_rows ? d_rows + (size_t)q * k : nullptr, d_scores ? d_scores + (size_t)q * k : nullptr, d_counts ? d_counts + q : nullptr);
-        if (rc) return rc;
-    }
-    return CGVEC_OK;
-}
-
-int tensor_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
-                 uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    if (ix->world == 1) return local_tensor(ix, c, d_q, qstride, nq, k, st, nullptr, d_rows, d_scores, d_counts);
-    uint64_t* local_keys = nullptr;
-    int rc = ensure_gather(ix, c, nq, k, &local_keys);
-    if (rc) return rc;
-    rc = local_tensor(ix, c, d_q, qstride, nq, k, st, local_keys, nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    return exchange_and_decode(ix, c, local_keys, nq, k, 0, st, d_rows, d_scores, d_counts);
-}
-
-// Runs nq queries (device, stride qstride) through whichever kernel family `path` selects, in batches.
-int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, int metric, int path, cudaStream_t st,
-                uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    bool tensor = false;
-    if (path == CGVEC_PATH_TENSOR) {
-        if (!tensor_path_applicable(ix, metric, nq)) return fail(CGVEC_ERR_UNSUPPORTED, "the tensor-core path serves the cosine metric");
-        tensor = true;
-    } else if (path == CGVEC_PATH_AUTO) {
-        const uint32_t min_nq = ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq;
-        tensor = tensor_path_applicable(ix, metric, nq) && nq >= min_nq && ix->n >= 4 * kTcCap && k <= kTcCap / 16;
-    }
-    uint32_t n_max = tensor ? tc_batch_limit(ix, nq) : 0;
-    if (tensor && n_max == 0) {
-        if (path == CGVEC_PATH_TENSOR) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
-        tensor = false;
-    }
-    uint32_t q0 = 0;
-    while (q0 < nq) {
-        uint32_t b;
-        int rc;
-        if (tensor) {
-            b = nq - q0 < n_max ? nq - q0 : n_max;
-            rc = tensor_batch(ix, c, d_q + (size_t)q0 * qstride, qstride, b, k, st, d_rows ? d_rows + (size_t)q0 * k : nullptr,
-                              d_scores ? d_scores + (size_t)q0 * k : nullptr, d_counts ? d_counts + q0 : nullptr);
-        } else {
-            b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
-            rc = scan_batch(ix, c, d_q + (size_t)q0 * qstride, b, k, metric, st, d_rows ? d_rows + (size_t)q0 * k : nullptr,
-                            d_scores ? d_scores + (size_t)q0 * k : nullptr, d_counts ? d_counts + q0 : nullptr);
-        }
-        if (rc) return rc;
-        q0 += b;
-    }
-    return CGVEC_OK;
-}
-
-void drain_timings(Index* ix) {
-    std::lock_guard<std::mutex> lk(ix->ev_mu);
-    for (auto& pr : ix->timed) {
-        if (cudaEventSynchronize(pr.second) == cudaSuccess) {
-            float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
-                ix->scan_ms_total += ms; ix->scan_timed++; ix->last_scan_ms = ms;
-            }
-        }
-        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
-    }
-    ix->timed.clear();
-}
-
-// Maps every rank's exchange buffer into this process (CUDA IPC over NVLink peer access).  Collective: all ranks call it.
-void setup_peer_exchange(Index* ix) {
-    ix->p2p = false;
-    if (ix->world > (int)kXchgMaxWorld) return;
-    bool ok = cudaMalloc(reinterpret_cast<void**>(&ix->xbuf), kXchgBytes) == cudaSuccess &&
-              cudaMemset(ix->xbuf, 0, kXchgBytes) == cudaSuccess;
-    cudaIpcMemHandle_t mine;
-    memset(&mine, 0, sizeof(mine));
-    if (ok) ok = cudaIpcGetMemHandle(&mine, ix->xbuf) == cudaSuccess;
-    // all-gather (handle, ok) so that every rank takes the same decision
-    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
-    std::vector<uint8_t> host(rec * ix->world, 0);
-    uint8_t* d_all = nullptr;
-    if (cudaMalloc(reinterpret_cast<void**>(&d_all), rec * ix->world) != cudaSuccess) { cudaGetLastError(); return; }
-    std::vector<uint8_t> me(rec, 0);
-    memcpy(me.data(), &mine, sizeof(mine));
-    me[sizeof(mine)] = ok ? 1 : 0;
-    cudaMemcpy(d_all + rec * ix->rank, me.data(), rec, cudaMemcpyHostToDevice);
-    bool gathered = nccl_api().AllGather(d_all + rec * ix->rank, d_all, rec, /*ncclUint8*/ 1, ix->comm, ix->main_stream) == kNcclSuccess &&
-                    cudaStreamSynchronize(ix->main_stream) == cudaSuccess &&
-                    cudaMemcpy(host.data(), d_all, rec * ix->world, cudaMemcpyDeviceToHost) == cudaSuccess;
-    cudaFree(d_all);
-    if (!gathered) { cudaGetLastError(); return; }
-    bool all_ok = true;
-    for (int r = 0; r < ix->world; ++r) all_ok = all_ok && host[rec * r + sizeof(mine)] == 1;
-    if (all_ok) {
-        for (int r = 0; r < ix->world && all_ok; ++r) {
-            if (r == ix->rank) { ix->xpeer[r] = ix->xbuf; continue; }
-            cudaIpcMemHandle_t h;
-            memcpy(&h, &host[rec * r], sizeof(h));
-            void* ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = false; break; }
-            ix->xpeer[r] = static_cast<uint8_t*>(ptr);
-        }
-    }
-    // second agreement round: only use peer memory if EVERY rank mapped every peer
-    uint8_t* d_flag = nullptr;
-    if (cudaMalloc(reinterpret_cast<void**>(&d_flag), ix->world) != cudaSuccess) { cudaGetLastError(); return; }
-    uint8_t f = all_ok ? 1 : 0;
-    cudaMemcpy(d_flag + ix->rank, &f, 1, cudaMemcpyHostToDevice);
-    std::vector<uint8_t> flags(ix->world, 0);
-    bool g2 = nccl_api().AllGather(d_flag + ix->rank, d_flag, 1, 1, ix->comm, ix->main_stream) == kNcclSuccess &&
-              cudaStreamSynchronize(ix->main_stream) == cudaSuccess &&
-              cudaMemcpy(flags.data(), d_flag, ix->world, cudaMemcpyDeviceToHost) == cudaSuccess;
-    cudaFree(d_flag);
-    bool every = g2;
-    for (int r = 0; r < ix->world; ++r) every = every && flags[r] == 1;
-    ix->p2p = every;
-    if (!every) cudaGetLastError();
-}
-
+#include "host_scan.inl"
+#include "host_tensor.inl"
 }  // namespace
 
 struct cgvec_index : Index {};
@@ -1769,3 +1169,4 @@ CGVEC_EXPORT int cgvec_get_trace(const cgvec_index* cix, uint64_t* out, uint32_t
 
 CGVEC_EXPORT const char* cgvec_last_error(void) { return g_err; }
 CGVEC_EXPORT const char* cgvec_version(void) { return "cgvec_b200 0.1.0 (sm_100a)"; }
+

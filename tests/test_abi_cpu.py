@@ -59,7 +59,7 @@ def test_product_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "codegraph-rust_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".rs")):
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h", ".hpp", ".cpp", ".rs")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "cgvec_oracle" not in txt, f
     out = subprocess.run(["ldd", os.path.join(pkg, "libcgvec_b200.so")], capture_output=True, text=True).stdout
