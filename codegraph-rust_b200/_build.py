@@ -69,6 +69,23 @@ def build_host_demo(force: bool = False) -> str:
     return DEMO
 
 
+MOCK_TEST = os.path.join(PKG, "host", "mock_backend_test")
+
+
+def build_mock_test(force: bool = False) -> str:
+    """CPU-only replay of the reference's MockBackend unit tests against the C++ host mirror (links the C ABI library
+    only because the header references its symbols; it never creates an index)."""
+    src = os.path.join(PKG, "host", "mock_backend_test.cpp")
+    hdr = os.path.join(PKG, "host", "cgvec_host.hpp")
+    if not force and _newer(MOCK_TEST, [src, hdr, LIB]):
+        return MOCK_TEST
+    cmd = ["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "host"), src, "-o", MOCK_TEST,
+           "-L", PKG, "-lcgvec_b200", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-lpthread"]
+    subprocess.run(cmd, check=True)
+    return MOCK_TEST
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_host_demo(force)
+    build_mock_test(force)

@@ -47,3 +47,11 @@ def test_host_mirror_matches_oracle(cg, oracle):
     assert np.float32([float.fromhex(s) for _, s in sem]).tobytes() == snorm.tobytes()
     assert lines["missing"] == "none"
     assert lines["baddim"] == str(cg.ERR_BAD_DIM)
+
+
+def test_reference_mock_backend_unit_tests_on_the_cpp_mirror(cg):
+    """surreal_store.rs:130-206 (MockBackend: id normalisation, embedding_2560 column, short-circuits) replayed on the
+    C++ SurrealVectorStore mirror — CPU only."""
+    exe = cg._build.build_mock_test()
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", p.stdout + p.stderr
