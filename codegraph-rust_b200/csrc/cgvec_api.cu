@@ -559,7 +559,10 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         memcpy(c->h_q + (size_t)q * qstride, queries + (size_t)q * ix->dim, ix->dim * sizeof(float));
         for (uint32_t i = ix->dim; i < qstride; ++i) c->h_q[(size_t)q * qstride + i] = 0.0f;
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_q, c->h_q, (size_t)nq * qstride * sizeof(float), cudaMemcpyHostToDevice, st));
+    {
+        cudaError_t e = cudaMemcpyAsync(c->d_q, c->h_q, (size_t)nq * qstride * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return finish(fail(CGVEC_ERR_CUDA, "query upload failed: %s", cudaGetErrorString(e)));
+    }
     {
         size_t oc = c->out_cap, oc2 = c->out_cap;
         rc = ensure(&c->d_rows, &oc, (size_t)nq * k); if (rc) return finish(rc);
@@ -577,7 +580,8 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         // posted PCIe writes from the last kernel replace three device-to-host copies per call.
         rc = run_queries(ix, c, c->d_q, qstride, nq, k, o.metric, o.path, st, c->h_rows, c->h_scores, c->h_counts);
         if (rc) return finish(rc);
-        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return finish(fail(CGVEC_ERR_CUDA, "search failed on the device: %s", cudaGetErrorString(e)));
     } else {
         if (ix->world > 1 || ix->row_offset != 0) return finish(fail(CGVEC_ERR_UNSUPPORTED, "non-SIMD formulas are not available on sharded indexes yet"));
         for (uint32_t q = 0; q < nq; ++q) {
