@@ -185,9 +185,14 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     // sorted exact keys [nq][kp] (needed by the proof) ...
     uint64_t* sorted = c->d_part[1];
     rc = merge_lists(ix, c, c->d_exact, nq, 1, kp, 0, sorted, nullptr, nullptr, nullptr, st, kp, kp, kp, /*sorted_in=*/0); if (rc) return rc;
-    // tensor accumulation + oracle accumulation; with TF32 the ROWS are truncated as well (<= 2^-10 relative each,
-    // the query's share is measured in rho): |err| <= (rho_q + 2^-10 + rho_q 2^-10) |q||r|.
-    const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f + (f32 ? 1.0e-3f : 0.0f);
+    // Error budget of the proof, all relative to |q||r| (cosine units):
+    //   (d+8) 2^-23      tensor-core accumulation of d exact products (allowing truncation instead of rounding)
+    //   (d/8+12) 2^-24   the oracle's own dot: d/8 fused steps per lane + horizontal sum + tail + division
+    //   2 (d/8+16) 2^-24 the two squared norms in oracle order, their square roots, rsqrtf (2 ulp) and the final multiply
+    //   rho_q            query rounding to the operand type, measured per query (Cauchy-Schwarz), added in the kernel
+    //   2^-10 (+ cross)  TF32 only: the tensor core drops 13 mantissa bits of the ROWS as well
+    const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f +
+                            2.0f * (float)(ix->dim / 8 + 16) * 5.9604645e-8f + (f32 ? 1.0e-3f : 0.0f);
     tc_verify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c->d_cand, kTcCap, d_cnt, kp, sorted, want ? want : 1, d_na, d_rho, acc_bound, METRIC_COSINE, nq,
                                                       d_proven, d_overflow);
     ix->launches++;
