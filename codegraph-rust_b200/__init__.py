@@ -394,6 +394,34 @@ class ParallelVectorOps:
     """simd_ops.rs:343-383"""
 
     @staticmethod
+    def parallel_batch_similarity(query, embeddings, device: int = 0) -> np.ndarray:
+        """simd_ops.rs:347-358 with similarity_fn = adaptive_cosine_similarity: one score per embedding, in order
+        (every score computed on the device in the reference's operation order)."""
+        emb = np.ascontiguousarray(embeddings, np.float32)
+        if emb.ndim != 2 or emb.shape[0] == 0:
+            return np.zeros(0, np.float32)
+        ix = Index(emb.shape[1], F32, device)
+        try:
+            ix.add(emb)
+            return ix.rescore(query, np.arange(emb.shape[0], dtype=np.uint64), COSINE, FORMULA_SIMD)
+        finally:
+            ix.close()
+
+    @staticmethod
+    def parallel_normalize_vectors(vectors, device: int = 0) -> np.ndarray:
+        """simd_ops.rs:386-419 -> normalize_avx2 per vector (returns the normalised copy; zero vectors stay zero)."""
+        v = np.ascontiguousarray(vectors, np.float32)
+        if v.ndim != 2 or v.shape[0] == 0:
+            return v.copy()
+        ix = Index(v.shape[1], F32, device)
+        try:
+            ix.add(v)
+            ix.normalize_rows()
+            return ix.get_rows(0, v.shape[0])
+        finally:
+            ix.close()
+
+    @staticmethod
     def parallel_top_k_search(query, embeddings, k: int, device: int = 0) -> List[Tuple[int, float]]:
         emb = np.ascontiguousarray(embeddings, np.float32)
         if emb.ndim != 2 or emb.shape[0] == 0:

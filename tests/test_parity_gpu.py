@@ -464,3 +464,15 @@ def test_symbol_resolver_argmax(cg, oracle):
     assert cg.resolve_symbol(ix, target, np.array([5, 77, 300], np.uint64)) is None       # nothing above the threshold
     assert cg.resolve_symbol(ix, target, np.array([], np.uint64)) is None
     ix.close()
+
+
+def test_parallel_vector_ops_mirror(cg, oracle):
+    """ParallelVectorOps::{parallel_batch_similarity, parallel_normalize_vectors} (simd_ops.rs:347-358, 386-419)."""
+    rng = np.random.default_rng(91)
+    emb = rng.standard_normal((500, 70)).astype(np.float32)
+    emb[3] = 0.0
+    q = rng.standard_normal(70).astype(np.float32)
+    sims = cg.ParallelVectorOps.parallel_batch_similarity(q, emb)
+    assert sims.tobytes() == oracle.scores(q, emb).tobytes()
+    norm = cg.ParallelVectorOps.parallel_normalize_vectors(emb)
+    assert norm.tobytes() == np.stack([oracle.normalize_avx2(r) for r in emb]).tobytes()
