@@ -158,3 +158,36 @@ def test_multi_device_placement_is_a_bijection(cg):
                     s2, l2 = cg.multi_locate(G, g + 1)
                     assert (s2 != s) or (l2 == l + 1)
             assert len(seen) == len(set(list(range(min(n, 3000))) + list(range(max(0, n - 3000), n))))
+
+
+def test_merge_topk_host_contract_with_ties_nan_and_short_lists(cg):
+    """Property check of cgvec_merge_topk_host against a brute-force sort under the result contract (best first, ties ->
+    lower row, NaN last, -0.0 == +0.0), for random partitions, duplicate scores, NaNs and lists shorter than k."""
+    rng = np.random.default_rng(123)
+    for trial in range(60):
+        parts = int(rng.integers(1, 7)); k = int(rng.integers(1, 12)); asc = bool(rng.integers(0, 2))
+        pool_scores = rng.choice(np.float32([0.0, -0.0, 0.25, 0.25, 0.5, -1.0, np.nan, 1.0, np.inf, -np.inf]), size=parts * k)
+        pool_scores = np.where(rng.random(parts * k) < 0.5, pool_scores, rng.standard_normal(parts * k).astype(np.float32)).astype(np.float32)
+        pool_rows = rng.permutation(parts * k * 3)[: parts * k].astype(np.uint64)
+
+        def key(i):
+            s = pool_scores[i]
+            if np.isnan(s):
+                return (1, 0.0, int(pool_rows[i]))
+            v = float(s) + 0.0
+            return (0, v if asc else -v, int(pool_rows[i]))
+
+        rows = np.zeros((parts, k), np.uint64); scores = np.zeros((parts, k), np.float32); counts = np.zeros(parts, np.uint32)
+        members = []
+        for p in range(parts):
+            idx = list(range(p * k, (p + 1) * k))
+            cnt = int(rng.integers(0, k + 1))
+            idx = sorted(idx, key=key)[:cnt]                       # each partial list is itself sorted under the contract
+            counts[p] = cnt
+            for j, i in enumerate(idx):
+                rows[p, j] = pool_rows[i]; scores[p, j] = pool_scores[i]
+            members += idx
+        want = sorted(members, key=key)[:k]
+        got_rows, got_scores = cg.merge_topk_host(rows, scores, counts, k, ascending=asc)
+        assert got_rows.tolist() == [int(pool_rows[i]) for i in want], (trial, asc)
+        assert np.array_equal(got_scores, np.float32([pool_scores[i] for i in want]), equal_nan=True)
