@@ -438,8 +438,8 @@ class ParallelVectorOps:
 class B200VectorStore:
     """trait VectorStore (codegraph-core/src/traits.rs:11-16) over one GPU-resident index."""
 
-    def __init__(self, dimension: int, dtype: int = F32, device: int = 0):
-        self.index = Index(dimension, dtype, device)
+    def __init__(self, dimension: int, dtype: int = F32, device: int = 0, devices: Optional[Sequence[int]] = None):
+        self.index = Index(dimension, dtype, device, devices=devices)
 
     def store_embeddings(self, nodes: Sequence[CodeNode]) -> None:
         withemb = [n for n in nodes if n.embedding is not None]       # nodes without an embedding are skipped

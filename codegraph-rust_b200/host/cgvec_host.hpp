@@ -83,6 +83,10 @@ public:
     explicit B200VectorStore(uint32_t dimension, cgvec_dtype storage = CGVEC_F32, int device = 0) : dim_(dimension) {
         check(cgvec_create(dimension, storage, &device, 1, &idx_));
     }
+    // one host process driving several GPUs: rows are dealt to the devices in blocks, searches merge over NVLink
+    B200VectorStore(uint32_t dimension, const std::vector<int>& devices, cgvec_dtype storage = CGVEC_F32) : dim_(dimension) {
+        check(cgvec_create(dimension, storage, devices.data(), (int)devices.size(), &idx_));
+    }
     ~B200VectorStore() override { cgvec_destroy(idx_); }
     B200VectorStore(const B200VectorStore&) = delete;
     B200VectorStore& operator=(const B200VectorStore&) = delete;
@@ -226,6 +230,52 @@ inline std::optional<std::pair<NodeId, float>> resolve_symbol(const B200VectorSt
         if (sims[i] > threshold && (!best || sims[i] > best->second)) best = std::make_pair(candidates[i], sims[i]);
     return best;
 }
+
+// GpuAcceleration (codegraph-vector/src/gpu.rs:109-381): the reference ships this API as a mock (upload sleeps, distances
+// are i*0.1 + query[0]*0.01); here the same two calls do the real thing.
+class GpuVectorData {
+public:
+    GpuVectorData(cgvec_index* idx, size_t count, size_t dimension) : idx_(idx), count_(count), dim_(dimension) {}
+    ~GpuVectorData() { cgvec_destroy(idx_); }
+    GpuVectorData(const GpuVectorData&) = delete;
+    GpuVectorData& operator=(const GpuVectorData&) = delete;
+    size_t vector_count() const { return count_; }
+    size_t dimension() const { return dim_; }
+    bool is_uploaded() const { return true; }
+    cgvec_index* handle() const { return idx_; }
+private:
+    cgvec_index* idx_;
+    size_t count_, dim_;
+};
+
+class GpuAcceleration {
+public:
+    explicit GpuAcceleration(int device = 0) : device_(device) {}
+    // upload_vectors(&[f32] flat, dimension) (gpu.rs:221-246)
+    std::unique_ptr<GpuVectorData> upload_vectors(const std::vector<float>& vectors, size_t dimension) const {
+        if (dimension == 0 || vectors.size() % dimension != 0) throw Error(CGVEC_ERR_BAD_ARG, "Vector data length not divisible by dimension");
+        cgvec_index* idx = nullptr;
+        int dev = device_;
+        check(cgvec_create((uint32_t)dimension, CGVEC_F32, &dev, 1, &idx));
+        const size_t n = vectors.size() / dimension;
+        int rc = cgvec_add(idx, nullptr, vectors.data(), n);
+        if (rc) { std::string msg = cgvec_last_error(); cgvec_destroy(idx); throw Error(rc, msg); }
+        return std::make_unique<GpuVectorData>(idx, n, dimension);
+    }
+    // compute_distances(query, data, limit) with the semantics of its CPU twin compute_distances_cpu (gpu.rs:297-322):
+    // cosine distance of the first `limit` uploaded vectors
+    std::vector<float> compute_distances(const std::vector<float>& query, const GpuVectorData& data, size_t limit) const {
+        if (query.size() != data.dimension())
+            throw Error(CGVEC_ERR_BAD_DIM, "Query dimension " + std::to_string(query.size()) + " doesn't match GPU data dimension " + std::to_string(data.dimension()));
+        std::vector<float> out(std::min(limit, data.vector_count()));
+        uint64_t n = 0;
+        check(cgvec_distances_first(data.handle(), query.data(), limit, out.data(), &n));
+        out.resize(n);
+        return out;
+    }
+private:
+    int device_;
+};
 
 struct SearchResult {
     NodeId node_id;

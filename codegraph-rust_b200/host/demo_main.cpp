@@ -47,6 +47,15 @@ int main(int argc, char** argv) {
         std::cout << "semantic";
         for (auto& r : sem.search_by_embedding(q, limit)) std::cout << " " << r.node_id.to_string() << ":" << std::hexfloat << r.score << std::defaultfloat;
         std::cout << "\n";
+        {
+            cgvec::GpuAcceleration gpu(0);
+            std::vector<float> flat;
+            for (size_t i = 0; i < 20; ++i) { auto e = hash_text_embedding("v" + std::to_string(i), dim); flat.insert(flat.end(), e.begin(), e.end()); }
+            auto data = gpu.upload_vectors(flat, dim);
+            std::cout << "gpu_distances";
+            for (float x : gpu.compute_distances(q, *data, 5)) std::cout << " " << std::hexfloat << x << std::defaultfloat;
+            std::cout << "\n";
+        }
         auto missing = store->get_embedding(cgvec::NodeId::from_u64(123456789));
         std::cout << "missing " << (missing ? "some" : "none") << "\n";
         try {

@@ -42,5 +42,17 @@ extern "C" {
     pub fn cgvec_rescore(
         idx: *const cgvec_index, query: *const f32, local_rows: *const u64, n: u32, metric: c_int, formula: c_int, out_scores: *mut f32,
     ) -> c_int;
+    pub fn cgvec_search_ex(
+        idx: *const cgvec_index, queries: *const f32, nq: u32, k: u32, opts: *const cgvec_search_opts,
+        out_rows: *mut u64, out_ids: *mut [u8; 16], out_scores: *mut f32, out_counts: *mut u32,
+    ) -> c_int;
+    pub fn cgvec_normalize_rows(idx: *mut cgvec_index) -> c_int;
+    pub fn cgvec_quantize_i8(idx: *mut cgvec_index) -> c_int;
+    pub fn cgvec_search_i8(
+        idx: *const cgvec_index, query: *const f32, limit: u32, out_rows: *mut u64, out_scores: *mut f32, out_count: *mut u32,
+    ) -> c_int;
+    pub fn cgvec_save_flat(idx: *const cgvec_index, path: *const c_char) -> c_int;
+    pub fn cgvec_load_flat(idx: *mut cgvec_index, path: *const c_char, out_rows_loaded: *mut u64) -> c_int;
+    pub fn cgvec_distances_first(idx: *const cgvec_index, query: *const f32, limit: u64, out: *mut f32, out_n: *mut u64) -> c_int;
     pub fn cgvec_last_error() -> *const c_char;
 }

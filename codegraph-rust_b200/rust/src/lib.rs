@@ -45,6 +45,29 @@ impl B200VectorStore {
         Ok(Self { h: Arc::new(Handle(raw)), dim: dimension })
     }
 
+    /// One process driving several GPUs (`cgvec_create` with n_devices > 1): rows are dealt to the devices in blocks and
+    /// every search merges the per-device results over NVLink.
+    pub fn with_devices(dimension: usize, devices: &[i32]) -> Result<Self> {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { ffi::cgvec_create(dimension as u32, ffi::CGVEC_F32, devices.as_ptr(), devices.len() as i32, &mut raw) })?;
+        Ok(Self { h: Arc::new(Handle(raw)), dim: dimension })
+    }
+
+    /// `SemanticSearch::calculate_similarity_score` for many candidates at once (search.rs:207-217, arithmetic :519-533).
+    pub fn rescore(&self, query: &[f32], node_ids: &[NodeId]) -> Result<Vec<f32>> {
+        let mut rows = Vec::with_capacity(node_ids.len());
+        for id in node_ids {
+            let mut row = 0u64;
+            check(unsafe { ffi::cgvec_row_of_id(self.h.0, id.as_bytes().as_ptr(), &mut row) })?;
+            rows.push(row);
+        }
+        let mut out = vec![0f32; rows.len()];
+        check(unsafe {
+            ffi::cgvec_rescore(self.h.0, query.as_ptr(), rows.as_ptr(), rows.len() as u32, ffi::CGVEC_COSINE, ffi::CGVEC_FORMULA_SEQ, out.as_mut_ptr())
+        })?;
+        Ok(out)
+    }
+
     fn knn(&self, query: Vec<f32>, limit: usize) -> Result<(Vec<NodeId>, Vec<f32>)> {
         if query.is_empty() || limit == 0 {
             return Ok((Vec::new(), Vec::new())); // surreal_store.rs:62-64

@@ -45,6 +45,9 @@ def test_host_mirror_matches_oracle(cg, oracle):
     sem = [t.rsplit(":", 1) for t in lines["semantic"].split()]
     assert [u for u, _ in sem] == [f"00000000-0000-0000-0000-{int(i) + 1:012x}" for i in si]
     assert np.float32([float.fromhex(s) for _, s in sem]).tobytes() == snorm.tobytes()
+    flat = np.stack([oracle.hash_text_embedding(f"v{i}", dim) for i in range(20)])
+    want_d = oracle.compute_distances_cpu(q, flat.reshape(-1), dim, 5)
+    assert np.float32([float.fromhex(x) for x in lines["gpu_distances"].split()]).tobytes() == want_d.tobytes()
     assert lines["missing"] == "none"
     assert lines["baddim"] == str(cg.ERR_BAD_DIM)
 
