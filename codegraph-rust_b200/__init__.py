@@ -525,6 +525,20 @@ def resolve_symbol(index: "Index", target_embedding, candidate_rows, threshold: 
     return best
 
 
+def resolve_symbols(index: "Index", target_embeddings, threshold: float = 0.75):
+    """The resolver's arg-max for U unresolved references at once, over ALL symbol rows of `index` instead of a trigram
+    prefilter (codegraph-mcp/src/indexer.rs:2673-2878 runs the U loop with rayon, :1914,1983): one k=1 scan per target
+    under the sequential cosine (search.rs:519-533), ties to the lower row = the reference's "first best wins" in row
+    order; entries at or below `threshold` become None.  -> [ (row, similarity) | None ] * U"""
+    t = np.ascontiguousarray(target_embeddings, np.float32)
+    if t.ndim == 1:
+        t = t[None, :]
+    if t.shape[0] == 0 or len(index) == 0:
+        return [None] * t.shape[0]
+    rows, sims, counts = index.search(t, 1, COSINE, formula=FORMULA_SEQ)
+    return [(int(rows[u, 0]), float(sims[u, 0])) if counts[u] and sims[u, 0] > threshold else None for u in range(t.shape[0])]
+
+
 class GpuAcceleration:
     """gpu.rs:109-381 API shape: upload_vectors(flat, dimension) -> data handle; compute_distances(query, data, limit)."""
 

@@ -466,6 +466,27 @@ def test_symbol_resolver_argmax(cg, oracle):
     ix.close()
 
 
+def test_symbol_resolver_batched_over_the_whole_index(cg, oracle):
+    """indexer.rs:2827-2843 arg-max for several unresolved references in one call, all symbols as candidates."""
+    rng = np.random.default_rng(2843)
+    embs = np.stack([oracle.hash_text_embedding(f"sym_{i}", 384) for i in range(3000)])
+    embs[1700] = embs[40]                                                       # duplicate symbol: the first one wins
+    targets = np.stack([embs[40], embs[2999] + np.float32(0.02) * rng.standard_normal(384).astype(np.float32),
+                        rng.standard_normal(384).astype(np.float32)])          # exact, near, unrelated
+    ix = cg.Index(384)
+    ix.add(embs)
+    got = cg.resolve_symbols(ix, targets)
+    for u in range(3):
+        wi, ws = oracle.inmemory_search_similar(targets[u], embs, 1)
+        if ws[0] > 0.75:
+            assert got[u] is not None and got[u][0] == int(wi[0]) and np.float32(got[u][1]).tobytes() == np.float32(ws[0]).tobytes()
+        else:
+            assert got[u] is None
+    assert got[0][0] == 40 and got[1][0] == 2999 and got[2] is None
+    assert cg.resolve_symbols(ix, np.zeros((0, 384), np.float32)) == []
+    ix.close()
+
+
 def test_parallel_vector_ops_mirror(cg, oracle):
     """ParallelVectorOps::{parallel_batch_similarity, parallel_normalize_vectors} (simd_ops.rs:347-358, 386-419)."""
     rng = np.random.default_rng(91)
