@@ -155,7 +155,7 @@ struct Index {
     std::vector<uint32_t> trace_kinds;      // 1 = scan, 2 = merge, 3 = exchange
     static constexpr uint32_t kTraceCap = 16384;
     int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 0, opt_tc_first = 0, opt_tc_kernel = 0, opt_tc_debug = 0, opt_tc2_max_n = kTc2MaxN;
-    int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0;
+    int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0, opt_tc_kbs = 0;
     std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
 
     // stats
@@ -229,16 +229,18 @@ int grow(Index* ix, uint64_t need, bool exact = false) {
     void* nrows = nullptr;
     float* nnorms = nullptr;
     size_t row_bytes = (size_t)ix->ld * ix->esize;
-    cudaError_t e = cudaMalloc(&nrows, newcap * row_bytes + 256);
+    const size_t slack = 8 * row_bytes + 256;                    // 4-D TMA boxes read whole 8-row groups: keep the last group mapped
+    cudaError_t e = cudaMalloc(&nrows, newcap * row_bytes + slack);
     if (e != cudaSuccess && newcap > need) {   // doubling did not fit: fall back to the exact size
         cudaGetLastError();
         newcap = need;
-        e = cudaMalloc(&nrows, newcap * row_bytes + 256);
+        e = cudaMalloc(&nrows, newcap * row_bytes + slack);
     }
     if (e != cudaSuccess) { cudaGetLastError(); return fail(CGVEC_ERR_OOM, "cudaMalloc of %zu bytes for %llu rows failed: %s", newcap * row_bytes, (unsigned long long)newcap, cudaGetErrorString(e)); }
     e = cudaMalloc(reinterpret_cast<void**>(&nnorms), (newcap + 64) * sizeof(float));
     if (e != cudaSuccess) { cudaGetLastError(); cudaFree(nrows); return fail(CGVEC_ERR_OOM, "cudaMalloc for norms failed: %s", cudaGetErrorString(e)); }
     CUDA_TRY(cudaMemsetAsync(nnorms, 0, (newcap + 64) * sizeof(float), ix->main_stream));
+    CUDA_TRY(cudaMemsetAsync(static_cast<uint8_t*>(nrows) + newcap * row_bytes, 0, slack, ix->main_stream));
     if (ix->n) {
         CUDA_TRY(cudaMemcpyAsync(nrows, ix->d_rows, ix->n * row_bytes, cudaMemcpyDeviceToDevice, ix->main_stream));
         CUDA_TRY(cudaMemcpyAsync(nnorms, ix->d_norms, ix->n * sizeof(float), cudaMemcpyDeviceToDevice, ix->main_stream));
@@ -1141,6 +1143,7 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "p2p") ix->opt_p2p = (int)value;
     else if (k == "tc_min_batch") ix->opt_tc_min_nq = (int)value;
     else if (k == "tc_stages") ix->opt_tc_stages = (int)value;
+    else if (k == "tc_kbs") ix->opt_tc_kbs = (int)value;
     else if (k == "tc_max_n") ix->opt_tc_max_n = (int)value;
     else if (k == "tc_margin") ix->opt_tc_margin = (int)value;
     else if (k == "tc_target") ix->opt_tc_target = (int)value;

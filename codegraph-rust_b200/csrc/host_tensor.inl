@@ -15,19 +15,33 @@ EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
-// 2-D fp16 tensor map, K (inner) x rows, 128-byte swizzle, box = 64 halves x box_rows, OOB reads as zero.
-int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows,
-                  int l2promo = 1, bool f32 = false) {
+// Tensor map over a row-major matrix of 128-byte K-blocks (64 halves or 32 floats), SWIZZLE_128B, OOB reads as zero.
+//   box4d == 0: 2-D {K, rows}, box = one K-block x box_rows                        (any row pitch that is a multiple of 16 bytes)
+//   box4d == 1: 4-D {128 B, 8 rows, K-blocks, row groups}, box = kbs K-blocks x box_rows: lands directly as kbs consecutive
+//               K-major swizzle atoms per 8-row group (UMMA SBO = kbs * 1024).  Needs row pitch % 128 == 0 (nkb * 128 <= pitch)
+//               and 7 rows of readable slack behind the last row (grow() provides it).
+int make_tmap_rows(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows,
+                   int l2promo, bool f32, uint32_t kbs, bool box4d) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t gdim[2] = {inner, rows};
-    cuuint64_t gstr[1] = {row_stride_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)(f32 ? kTcKBlock / 2 : kTcKBlock), box_rows};   // 128 bytes of K either way
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B,
-                    l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint32_t kbe = (cuuint32_t)(f32 ? kTcKBlock / 2 : kTcKBlock);       // 128 bytes of K either way
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapL2promotion promo = l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    CUresult r;
+    if (box4d) {
+        const uint64_t nkb = (inner + kbe - 1) / kbe;
+        cuuint64_t gdim[4] = {kbe, 8, nkb, (rows + 7) / 8};
+        cuuint64_t gstr[3] = {row_stride_bytes, 128, 8 * row_stride_bytes};
+        cuuint32_t box[4] = {kbe, 8, kbs, box_rows / 8};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = fn(map, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t gdim[2] = {inner, rows};
+        cuuint64_t gstr[1] = {row_stride_bytes};
+        cuuint32_t box[2] = {kbe, box_rows};
+        cuuint32_t estr[2] = {1, 1};
+        r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return fail(CGVEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CGVEC_OK;
 }
@@ -38,35 +52,52 @@ bool tensor_path_applicable(const Index* ix, int metric, uint32_t nq) {
     return metric == CGVEC_COSINE && nq >= 1 && ix->n >= 1;      // f16 rows -> kind::f16, f32 rows -> kind::tf32
 }
 
-// Largest MMA N (multiple of 16) whose resident query block leaves >= 3 row stages in shared memory (tc_scan_kernel).
-uint32_t tc_max_n(const Index* ix, uint32_t* stages_out) {
+// Launch plan of the tensor kernels for a batch padded to N columns: kernel (resident query block vs CTA pairs), K-blocks
+// per ring stage and ring depth.  Measured (tools/tma_stream_bench.cu, profiles/r02_tma_stream_pipe.txt): one commit per
+// 16 KB K-block caps the ring at 5.2 TB/s whatever its depth, two or four K-blocks per stage reach 6.8-7.1 TB/s.
+struct TcPlan { bool pairs; uint32_t N, nkb, kbs, groups, stages, box4d, smem; };
+bool tc_plan_fill(const Index* ix, bool pairs, uint32_t N, TcPlan* out) {
     const uint32_t kbe = ix->dtype == CGVEC_F32 ? kTcKBlock / 2 : kTcKBlock;
     const uint32_t nkb = (ix->dim + kbe - 1) / kbe;
+    const bool can4d = ((size_t)ix->ld * ix->esize) % 128 == 0 && ix->opt_tc_kbs != 1 && nkb > 1;
+    const uint32_t try_kbs[3] = {ix->opt_tc_kbs > 0 ? (uint32_t)ix->opt_tc_kbs : 2u, 2u, 1u};
+    for (int t = 0; t < 3; ++t) {
+        uint32_t kbs = can4d ? try_kbs[t] : 1u;
+        if (kbs > nkb) kbs = nkb;
+        if (kbs < 1) kbs = 1;
+        const uint32_t min_stages = pairs ? 2u : 3u;
+        uint32_t max_stages = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : (kbs >= 4 ? 3u : kbs >= 2 ? 6u : 12u);
+        if (max_stages > kTcMaxStages) max_stages = kTcMaxStages;
+        for (uint32_t s = max_stages; s >= min_stages; --s) {
+            const uint32_t total = (pairs ? tc2_smem_layout(N, s, kbs).total : tc_smem_layout(N, nkb, s, kbs).total) + 1024;
+            if (total <= kSmemBudget) {
+                out->pairs = pairs; out->N = N; out->nkb = nkb; out->kbs = kbs; out->groups = (nkb + kbs - 1) / kbs; out->stages = s;
+                out->box4d = kbs > 1 ? 1u : 0u; out->smem = total;
+                return true;
+            }
+        }
+        if (!can4d) break;
+    }
+    return false;
+}
+// Largest MMA N (multiple of 16) whose resident query block still leaves a ring in shared memory (tc_scan_kernel).
+uint32_t tc_max_n(const Index* ix) {
     uint32_t limit = (uint32_t)ix->opt_tc_max_n;
     if (limit > kTcMaxN) limit = kTcMaxN;
-    for (uint32_t N = limit & ~15u; N >= 16; N -= 16) {
-        for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s) {
-            if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { if (stages_out) *stages_out = s; return N; }
-            if (ix->opt_tc_stages) break;
-        }
-    }
-    return 0;
-}
-// tc2_scan_kernel (CTA pairs) streams the query block: any N <= 256 fits; stages follow from N.
-uint32_t tc2_stages(const Index* ix, uint32_t N) {
-    for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 12; s >= 2; --s)
-        if (tc2_smem_layout(N, s).total + 1024 <= kSmemBudget) return s;
+    TcPlan pl;
+    for (uint32_t N = limit & ~15u; N >= 16; N -= 16)
+        if (tc_plan_fill(ix, false, N, &pl)) return N;
     return 0;
 }
 // which kernel serves a batch of nq queries, and how many queries one pass may take
 bool tc_use_pairs(const Index* ix, uint32_t nq) {
     if (ix->opt_tc_kernel == 1) return false;
     if (ix->opt_tc_kernel == 2) return true;
-    return nq > tc_max_n(ix, nullptr);
+    return nq > tc_max_n(ix);
 }
 uint32_t tc_batch_limit(const Index* ix, uint32_t nq) {
     if (tc_use_pairs(ix, nq)) { uint32_t m = (uint32_t)ix->opt_tc2_max_n & ~15u; return m >= 16 && m <= kTc2MaxN ? m : kTc2MaxN; }
-    return tc_max_n(ix, nullptr);
+    return tc_max_n(ix);
 }
 
 // Tensor-core scan of the local shard for `nq` <= N_max queries (f32, on the device, stride qstride): approximate
@@ -81,20 +112,14 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
         if (arc) return arc;
     }
     const bool pairs = tc_use_pairs(ix, nq);
-    uint32_t stages = 0;
-    const uint32_t n_max = pairs ? kTc2MaxN : tc_max_n(ix, &stages);
+    const uint32_t n_max = pairs ? kTc2MaxN : tc_max_n(ix);
     if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
     const uint32_t N = (nq + 15) & ~15u;
     const bool f32 = ix->dtype == CGVEC_F32;
+    TcPlan plan;
+    if (!tc_plan_fill(ix, pairs, N, &plan)) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the tensor kernel at N = %u, dimension %u", N, ix->dim);
     const uint32_t kbe = f32 ? kTcKBlock / 2 : kTcKBlock;            // elements per 128-byte K-block
-    const uint32_t nkb = (ix->dim + kbe - 1) / kbe, dpad = nkb * kbe;
-    if (pairs) {
-        stages = tc2_stages(ix, N);
-        if (stages < 2) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the paired tensor kernel at N = %u", N);
-    } else {   // more stages when the query block is small
-        for (uint32_t s = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : 8; s >= 3; --s)
-            if (tc_smem_layout(N, nkb, s).total + 1024 <= kSmemBudget) { stages = s; break; }
-    }
+    const uint32_t nkb = plan.nkb, dpad = nkb * kbe, stages = plan.stages;
     const uint32_t tile_rows = pairs ? 2 * kTcTileRows : kTcTileRows;
     const uint64_t n = ix->n;
     const uint32_t want = (uint32_t)(k < n ? k : n);
@@ -118,19 +143,21 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     CUDA_TRY(cudaGetLastError());
 
     CUtensorMap tmA, tmB;
-    rc = make_tmap_f16(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * ix->esize, kTcTileRows, ix->opt_tc_l2promo, f32); if (rc) return rc;
-    rc = make_tmap_f16(&tmB, c->d_B, dpad, N, (uint64_t)dpad * ix->esize, pairs ? N / 2 : N, 1, f32); if (rc) return rc;
+    rc = make_tmap_rows(&tmA, ix->d_rows, ix->dim, n, (uint64_t)ix->ld * ix->esize, kTcTileRows, ix->opt_tc_l2promo, f32, plan.kbs, plan.box4d != 0); if (rc) return rc;
+    if (pairs) rc = make_tmap_rows(&tmB, c->d_B, dpad, N, (uint64_t)dpad * ix->esize, N / 2, 1, f32, plan.kbs, plan.box4d != 0);
+    else rc = make_tmap_rows(&tmB, c->d_B, dpad, N, (uint64_t)dpad * ix->esize, N, 1, f32, 1, false);
+    if (rc) return rc;
 
     TcParams p{};
     ScanParams map = map_params(ix);
     p.n_rows = n; p.norms = ix->d_norms; p.thr = d_thr; p.cand = c->d_cand; p.cand_count = d_cnt; p.overflow = d_overflow;
     p.cap = kTcCap; p.nq = nq; p.N = N; p.nkb = nkb; p.stages = stages; p.metric = METRIC_COSINE;
+    p.kbs = plan.kbs; p.groups = plan.groups; p.box4d = plan.box4d;
     p.tmem_cols = next_pow2(2 * N) < 32 ? 32 : next_pow2(2 * N);
-    p.prefetch_dist = (uint32_t)ix->opt_tc_prefetch;
     p.debug = (uint32_t)ix->opt_tc_debug;
     p.tf32 = f32 ? 1u : 0u;
     p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
-    const uint32_t smem = (pairs ? tc2_smem_layout(N, stages).total : tc_smem_layout(N, nkb, stages).total) + 1024;
+    const uint32_t smem = plan.smem;
 
     // geometric row ranges: after T rows the threshold sits at quantile kp/T, so a range of S rows adds about
     // S*kp/T survivors; ranges are sized to keep each list near `target` entries (small sorts in tc_select_kernel)

@@ -29,16 +29,17 @@
 
 namespace cgv {
 
-constexpr int kTcThreads = 384;               // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: TMA; 5: MMA; 6: TMEM alloc
+constexpr int kTcThreads = 384;               // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: TMA; 5: MMA; 6: TMEM alloc; 7: spare
 constexpr int kTcTileRows = 128;
 constexpr int kTcKBlock = 64;                 // halves per 128-byte swizzle row
-constexpr int kTcStageBytes = kTcTileRows * 128;
+constexpr int kTcKBlockBytes = kTcTileRows * 128;   // one K-block of a 128-row tile: 16 KB
 constexpr int kTcMaxN = 128;                // tc_scan_kernel (resident query block)
 constexpr int kTc2MaxN = 256;               // tc2_scan_kernel (CTA pairs, streamed query block)
+constexpr int kTcMaxStages = 12;
 
 struct TcParams {
     uint64_t n_rows;            // local rows of the shard (rows >= n_rows are TMA zero fill and masked)
-    uint64_t row_begin, row_end;   // this launch scans local rows [row_begin, row_end); row_begin % 128 == 0
+    uint64_t row_begin, row_end;   // this launch scans local rows [row_begin, row_end); row_begin % 256 == 0
     const float* norms;         // squared row norms (reference order); cosine only
     const float* thr;           // [N] per-query thresholds in dot/|row| units
     uint64_t* cand;             // [N][cap] candidate keys
@@ -47,23 +48,27 @@ struct TcParams {
     uint32_t cap;
     uint32_t nq;                // real queries (<= N)
     uint32_t N;                 // MMA N: nq rounded up to 16
-    uint32_t nkb;               // ceil(d / 64)
+    uint32_t nkb;               // 128-byte K-blocks per row: ceil(d / 64) halves or ceil(d / 32) floats
+    uint32_t kbs;               // K-blocks per ring stage: one TMA box, one tcgen05.commit
+    uint32_t groups;            // ceil(nkb / kbs) stages per row tile
+    uint32_t box4d;             // 1: 4-D boxes {128 B, 8 rows, kbs K-blocks, row groups} (row pitch % 128 == 0); 0: 2-D boxes, kbs == 1
     uint32_t stages;
     uint32_t metric;            // METRIC_COSINE or METRIC_DOT
     uint32_t tmem_cols;         // power of two >= 2*N, >= 32
-    uint32_t prefetch_dist;     // K-blocks of L2 prefetch issued ahead of the demand loads (0 = off)
     uint32_t tf32;              // 0: f16 rows/queries (kind::f16, 64 elements per 128-byte K-block); 1: f32 rows/queries as TF32 (kind::tf32, 32)
     uint32_t debug;             // bit 0: skip the MMAs, bit 1: skip the epilogue body (bandwidth triage only; results invalid)
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
 };
 
-struct TcSmemLayout { uint32_t off_b, off_a, off_bars, off_misc, off_thr, total; };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(uint32_t N, uint32_t nkb, uint32_t stages) {
+// Shared-memory plan of tc_scan_kernel: resident query block | ring of row stages | barriers | misc | thresholds
+struct TcSmemLayout { uint32_t off_b, off_a, stage_bytes, off_bars, off_misc, off_thr, total; };
+__host__ __device__ inline TcSmemLayout tc_smem_layout(uint32_t N, uint32_t nkb, uint32_t stages, uint32_t kbs) {
     TcSmemLayout L;
     L.off_b = 0;
     L.off_a = nkb * N * 128;                                   // multiple of 1024 because N % 8 == 0
-    L.off_bars = L.off_a + stages * kTcStageBytes;
+    L.stage_bytes = kbs * kTcKBlockBytes;
+    L.off_bars = L.off_a + stages * L.stage_bytes;
     L.off_misc = L.off_bars + (2 * stages + 1 + 4) * 8;        // tmem base address
     L.off_thr = (L.off_misc + 16 + 15) & ~15u;                 // negated thresholds, 16-byte aligned for LDS.128
     L.total = L.off_thr + N * 4;
@@ -81,16 +86,29 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
                  : "memory");
 }
-// L2 prefetch of one TMA box: keeps DRAM requests in flight far beyond what the shared-memory ring can hold
-// (the resident query block leaves only ~96 KB of stages), so the demand loads that follow mostly hit in L2.
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+// 4-D box {128 bytes of K, 8 rows, kbs K-blocks, row groups}: one instruction lands kbs K-blocks of a row tile as kbs
+// consecutive SWIZZLE_128B atoms per 8-row group, i.e. K-major operand tiles with a stride of kbs*1024 bytes between
+// 8-row groups (the SBO of the UMMA descriptor).
+__device__ __forceinline__ void tma_load_4d_hint(void* dst, const CUtensorMap* map, int c2, int c3, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(c2), "r"(c3), "l"(pol)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of the (converged) warp: the single-thread roles run their loops warp-wide and issue under this predicate, so
+// that ring positions, descriptors and barrier addresses stay in uniform registers.  (Issuing from `if (lane == 0)` makes
+// every operand thread-divergent for the compiler: it then wraps each tcgen05.mma in an R2UR waterfall loop, ~16
+// instructions per MMA on the kernel's critical thread.)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_warp_id() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -99,17 +117,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
-// LBO>>4 [16,30) (ignored for swizzled K-major, 1), SBO>>4 [32,46) = 1024 B between 8-row groups, version 1
-// [46,48), layout type SWIZZLE_128B = 2 at [61,64).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
+// LBO>>4 [16,30) (ignored for swizzled K-major, 1), SBO>>4 [32,46) = bytes between 8-row groups, version 1
+// [46,48), layout type SWIZZLE_128B = 2 at [61,64).  The MMA issuer keeps the two halves apart: the high word is a
+// per-launch constant, the low word (start address) advances by 2 per 32 bytes of K and by 64 per K-block.
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) { return umma_desc(umma_desc_lo(smem_addr), umma_desc_hi(1024)); }
 // kind::f16 instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ inline uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -118,37 +132,30 @@ __host__ __device__ inline uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
 __host__ __device__ inline uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T.  TF32 / PAIR are compile-time: the issuing thread's loop carries no branches.
+template <bool TF32, bool PAIR>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32 && PAIR)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (TF32)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (PAIR)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_t(uint64_t* bar) { if (PAIR) umma_commit_2sm(bar); else umma_commit(bar); }
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -156,61 +163,77 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.wait::ld with the loaded registers as in/out operands: every later use of r[] is data-dependent on the wait,
+// so the compiler cannot schedule arithmetic on them ahead of it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 
 // ---- epilogue of one 128-row accumulator tile (shared by both kernels) ----------------------------------------------
-// Each thread owns one row (TMEM lane) and walks the N query columns 16 at a time.  Fast path per column: one FFMA
-// (acc * 1/|row| - thr, thresholds pre-negated in shared memory, LDS.128) and one FMNMX into a running maximum; a
+// Each thread owns one row (TMEM lane) and walks its share of the N query columns 16 at a time through two
+// register buffers that are indexed statically (a dynamically indexed buffer would live in local memory: the
+// first version of this epilogue spent a quarter of the kernel in STL/LDL round trips).  Fast path per column: one FFMA
+// (acc * 1/|row| - thr, thresholds pre-negated in shared memory, LDS.128) and a share of a 3-input AND of sign bits; a
 // single ballot per 16 columns decides whether ANY lane has a survivor.  Only then (rare once thresholds have
 // tightened) the slow path reserves list slots with warp-aggregated atomics and writes the keys.
-__device__ __forceinline__ void tmem_ld_x16_nowait(uint32_t taddr, uint32_t* r) { tmem_ld_x16(taddr, r); }
+__device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint32_t (&r)[16], const float* __restrict__ s_nthr, uint32_t c0,
+                                                  uint64_t row, bool valid, float inv, uint32_t lane) {
+    float t[16];
+    uint32_t all_neg = 0x80000000u;                                   // sign bit survives iff every t[j] is negative
+#pragma unroll
+    for (uint32_t j4 = 0; j4 < 4; ++j4) {
+        const float4 nt = *reinterpret_cast<const float4*>(s_nthr + c0 + 4 * j4);
+        t[4 * j4 + 0] = __fmaf_rn(__uint_as_float(r[4 * j4 + 0]), inv, nt.x);
+        t[4 * j4 + 1] = __fmaf_rn(__uint_as_float(r[4 * j4 + 1]), inv, nt.y);
+        t[4 * j4 + 2] = __fmaf_rn(__uint_as_float(r[4 * j4 + 2]), inv, nt.z);
+        t[4 * j4 + 3] = __fmaf_rn(__uint_as_float(r[4 * j4 + 3]), inv, nt.w);
+        all_neg &= __float_as_uint(t[4 * j4 + 0]) & __float_as_uint(t[4 * j4 + 1]);
+        all_neg &= __float_as_uint(t[4 * j4 + 2]) & __float_as_uint(t[4 * j4 + 3]);
+    }
+    const bool maybe = valid && !(all_neg & 0x80000000u);
+    if (__ballot_sync(0xffffffffu, maybe) == 0u) return;
+    // ---- slow path: reserve slots for all 16 columns first (independent atomics in flight), then write
+    uint32_t masks[16], base[16];
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        masks[j] = __ballot_sync(0xffffffffu, valid && t[j] >= 0.0f);
+        base[j] = 0;
+        if (masks[j] && (int)lane == __ffs(masks[j]) - 1) base[j] = atomicAdd(&p.cand_count[c0 + j], (uint32_t)__popc(masks[j]));
+    }
+    const uint64_t b = row / p.blk_rows, rr = row - b * p.blk_rows;
+    const uint32_t g = (uint32_t)((b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        if (masks[j]) {
+            const uint32_t bj = __shfl_sync(0xffffffffu, base[j], __ffs(masks[j]) - 1);
+            if (masks[j] & (1u << lane)) {
+                const uint32_t pos = bj + __popc(masks[j] & ((1u << lane) - 1));
+                if (pos < p.cap) p.cand[(size_t)(c0 + j) * p.cap + pos] = make_key(__uint_as_float(r[j]) * inv, g, false);
+                else *p.overflow = 1u;
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t taddr, const float* __restrict__ s_nthr, uint64_t row,
                                                  bool valid, float inv, uint32_t lane, uint32_t col_begin, uint32_t col_end) {
     if ((p.debug & 2u) || col_begin >= col_end) return;
-    uint32_t r[2][16];
-    tmem_ld_x16(taddr + col_begin, r[0]);
-    tmem_ld_wait();
-    uint32_t cur = 0;
-    for (uint32_t c0 = col_begin; c0 < col_end; c0 += 16, cur ^= 1u) {
-        if (c0 + 16 < col_end) tmem_ld_x16(taddr + c0 + 16, r[cur ^ 1u]);   // next 16 columns stream in behind the compares
-        float t[16];
-        uint32_t all_neg = 0x80000000u;                                   // sign bit survives iff every t[j] is negative
-#pragma unroll
-        for (uint32_t j4 = 0; j4 < 4; ++j4) {
-            const float4 nt = *reinterpret_cast<const float4*>(s_nthr + c0 + 4 * j4);
-            t[4 * j4 + 0] = __fmaf_rn(__uint_as_float(r[cur][4 * j4 + 0]), inv, nt.x);
-            t[4 * j4 + 1] = __fmaf_rn(__uint_as_float(r[cur][4 * j4 + 1]), inv, nt.y);
-            t[4 * j4 + 2] = __fmaf_rn(__uint_as_float(r[cur][4 * j4 + 2]), inv, nt.z);
-            t[4 * j4 + 3] = __fmaf_rn(__uint_as_float(r[cur][4 * j4 + 3]), inv, nt.w);
-            all_neg &= __float_as_uint(t[4 * j4 + 0]) & __float_as_uint(t[4 * j4 + 1]) & __float_as_uint(t[4 * j4 + 2]) & __float_as_uint(t[4 * j4 + 3]);
+    uint32_t ra[16], rb[16];
+    tmem_ld_x16(taddr + col_begin, ra);
+    for (uint32_t c0 = col_begin; c0 < col_end; c0 += 32) {
+        tmem_ld_wait(ra);
+        const bool more = c0 + 16 < col_end;
+        if (more) tmem_ld_x16(taddr + c0 + 16, rb);                       // next 16 columns stream in behind the compares
+        tc_epilogue_chunk(p, ra, s_nthr, c0, row, valid, inv, lane);
+        if (more) {
+            tmem_ld_wait(rb);
+            if (c0 + 32 < col_end) tmem_ld_x16(taddr + c0 + 32, ra);
+            tc_epilogue_chunk(p, rb, s_nthr, c0 + 16, row, valid, inv, lane);
         }
-        const bool maybe = valid && !(all_neg & 0x80000000u);
-        const uint32_t hit = __ballot_sync(0xffffffffu, maybe);
-        if (hit) {
-            // ---- slow path: reserve slots for all 16 columns first (independent atomics in flight), then write
-            uint32_t masks[16], base[16];
-#pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) {
-                masks[j] = __ballot_sync(0xffffffffu, valid && t[j] >= 0.0f);
-                base[j] = 0;
-                if (masks[j] && (int)lane == __ffs(masks[j]) - 1) base[j] = atomicAdd(&p.cand_count[c0 + j], (uint32_t)__popc(masks[j]));
-            }
-            const uint64_t b = row / p.blk_rows, rr = row - b * p.blk_rows;
-            const uint32_t g = (uint32_t)((b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);
-#pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) {
-                if (masks[j]) {
-                    const uint32_t bj = __shfl_sync(0xffffffffu, base[j], __ffs(masks[j]) - 1);
-                    if (masks[j] & (1u << lane)) {
-                        const uint32_t pos = bj + __popc(masks[j] & ((1u << lane) - 1));
-                        if (pos < p.cap) p.cand[(size_t)(c0 + j) * p.cap + pos] = make_key(__uint_as_float(r[cur][j]) * inv, g, false);
-                        else *p.overflow = 1u;
-                    }
-                }
-            }
-        }
-        tmem_ld_wait();
     }
 }
 
@@ -219,13 +242,64 @@ __device__ __forceinline__ void tc_stage_thresholds(const TcParams& p, float* s_
     for (uint32_t j = tid; j < p.N; j += nthreads) s_nthr[j] = j < p.nq ? -p.thr[j] : __int_as_float(0xff800000);
 }
 
+// ---- MMA issue loop (one elected thread) ------------------------------------------------------------------------------
+// Per ring stage: wait for the bytes, 4 MMAs (K = 16 halves / 8 floats each) per K-block of the stage, ONE commit.  The
+// thread's instruction stream is the bottleneck of the whole kernel when it is not lean (the first version rebuilt both
+// 64-bit descriptors and branched on the operand kind per MMA and issued one commit per K-block: the tensor pipe sat at
+// 50 %), so: operand kind and pairing are template parameters, descriptor high words are loop constants, low words are
+// advanced with adds, and the ring position is a counter (no division).
+//   a_lo0            descriptor low word of stage 0's A tile; stage s is (s * stage_bytes) >> 4 further
+//   b_resident_lo0   resident query block (tc_scan_kernel): low word of K-block 0, K-block kb is (kb * N * 128) >> 4 further
+//   b_in_stage_off   streamed query block (tc2_scan_kernel): byte offset of the B part inside a stage
+template <bool TF32, bool PAIR>
+__device__ __forceinline__ void tc_issue_loop(const TcParams& p, uint64_t my_tiles, uint32_t tmem_base, uint32_t a_lo0, uint32_t stage_bytes,
+                                              uint32_t b_resident_lo0, uint32_t b_in_stage_off, uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar) {
+    const uint32_t M = PAIR ? 2 * kTcTileRows : kTcTileRows;
+    const uint32_t idesc = TF32 ? umma_idesc_tf32(M, p.N) : umma_idesc_f16(M, p.N);
+    const uint32_t hi_stage = umma_desc_hi(p.kbs * 1024), hi_res = umma_desc_hi(1024);
+    const uint32_t stage_step = stage_bytes >> 4, b_kb_step = PAIR ? 64u : (p.N * 128u) >> 4;
+    const uint32_t skip_mma = p.debug & 1u;
+    uint32_t s = 0, ph = 0, a_lo = a_lo0;
+    for (uint64_t t = 0; t < my_tiles; ++t) {
+        const uint32_t buf = t & 1;
+        mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * p.N;
+        uint32_t kb = 0;
+        for (uint32_t g = 0; g < p.groups; ++g) {
+            mbar_wait(&full_bar[s], ph);                              // TMA bytes have landed
+            tc_fence_after();
+            const uint32_t nk = min(p.kbs, p.nkb - kb);
+            uint32_t al = a_lo;
+            uint32_t bl = PAIR ? a_lo + (b_in_stage_off >> 4) : b_resident_lo0 + kb * b_kb_step;
+            const uint32_t bh = PAIR ? hi_stage : hi_res;
+            if (elect_one()) {
+                if (!skip_mma) {
+                    for (uint32_t i = 0; i < nk; ++i, al += 64, bl += b_kb_step) {
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_ss<TF32, PAIR>(d_tmem, umma_desc(al + 2 * k, hi_stage), umma_desc(bl + 2 * k, bh), idesc, (kb + i) | k);
+                    }
+                }
+                umma_commit_t<PAIR>(&empty_bar[s]);                    // stage free once these MMAs retire
+                if (g + 1 == p.groups) umma_commit_t<PAIR>(&tfull_bar[buf]);   // accumulator complete
+            }
+            __syncwarp();
+            kb += nk;
+            a_lo += stage_step;
+            if (++s == p.stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+        }
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window; the launch reserves 1 KB of slack for this
     uint8_t* smem = smem_tc_raw + ((1024u - (smem_u32(smem_tc_raw) & 1023u)) & 1023u);
-    const TcSmemLayout lay = tc_smem_layout(p.N, p.nkb, p.stages);
+    const TcSmemLayout lay = tc_smem_layout(p.N, p.nkb, p.stages, p.kbs);
     uint8_t* sB = smem + lay.off_b;
     uint8_t* sA = smem + lay.off_a;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
@@ -235,7 +309,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty_bar = tfull_bar + 2;     // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + lay.off_misc);
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
     const uint64_t first_tile = p.row_begin / kTcTileRows;
     const uint64_t num_tiles = (p.row_end - p.row_begin + kTcTileRows - 1) / kTcTileRows;
     const uint64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -258,68 +332,42 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-wide loop, one elected lane issues) =====================
+        const uint64_t pol = l2_policy_evict_first();
+        const int kbe = p.tf32 ? kTcKBlock / 2 : kTcKBlock;           // elements per 128-byte K-block
+        if (elect_one()) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
-            const uint64_t pol = l2_policy_evict_first();
             mbar_arrive_expect_tx(b_bar, p.nkb * p.N * 128);
-            const int kbe = p.tf32 ? kTcKBlock / 2 : kTcKBlock;       // elements per 128-byte K-block
             for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.N * 128, &tmB, kb * kbe, 0, b_bar);
-            const uint64_t total_it = my_tiles * p.nkb;
-            auto prefetch_block = [&](uint64_t j) {
-                const uint64_t t = j / p.nkb;
-                const uint32_t kb = (uint32_t)(j - t * p.nkb);
-                tma_prefetch_2d(&tmA, kb * kbe, (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows));
-            };
-            for (uint64_t j = 0; j < p.prefetch_dist && j < total_it; ++j) prefetch_block(j);
-            uint64_t it = 0;
-            for (uint64_t t = 0; t < my_tiles; ++t) {
-                const int row0 = (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows);
-                for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
-                    if (p.prefetch_dist && it + p.prefetch_dist < total_it) prefetch_block(it + p.prefetch_dist);
-                    const uint32_t s = it % p.stages;
-                    if (it >= p.stages) mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
-                    mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
-                    tma_load_2d_hint(sA + (size_t)s * kTcStageBytes, &tmA, kb * kbe, row0, &full_bar[s], pol);
+        }
+        __syncwarp();
+        uint32_t s = 0, ph = 1;
+        for (uint64_t t = 0; t < my_tiles; ++t) {
+            const int row0 = (int)((first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows);
+            for (uint32_t g = 0; g < p.groups; ++g) {
+                mbar_wait(&empty_bar[s], ph);                            // passes at once during the first trip round the ring
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_bar[s], lay.stage_bytes);
+                    uint8_t* dst = sA + (size_t)s * lay.stage_bytes;
+                    if (p.box4d) tma_load_4d_hint(dst, &tmA, (int)(g * p.kbs), row0 >> 3, &full_bar[s], pol);
+                    else tma_load_2d_hint(dst, &tmA, (int)g * kbe, row0, &full_bar[s], pol);
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kTcTileRows, p.N) : umma_idesc_f16(kTcTileRows, p.N);
-            mbar_wait(b_bar, 0);
-            tc_fence_after();
-            uint64_t it = 0;
-            for (uint64_t t = 0; t < my_tiles; ++t) {
-                const uint32_t buf = t & 1;
-                mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * p.N;
-                for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
-                    const uint32_t s = it % p.stages;
-                    mbar_wait(&full_bar[s], (it / p.stages) & 1);        // TMA bytes have landed
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kTcStageBytes);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)kb * p.N * 128);
-                    if (!(p.debug & 1u)) {
-#pragma unroll
-                        for (uint32_t k = 0; k < kTcKBlock / 16; ++k) {      // 4 MMAs per 128-byte K-block: K = 16 halves or 8 tf32 each
-                            if (p.tf32) umma_tf32_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
-                            else umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
-                        }
-                    }
-                    umma_commit(&empty_bar[s]);                          // stage free once these MMAs retire
-                }
-                umma_commit(&tfull_bar[buf]);                            // accumulator complete
-            }
-        }
+        // ===================== MMA issuer (warp-wide loop, one elected lane issues) =====================
+        mbar_wait(b_bar, 0);
+        tc_fence_after();
+        if (p.tf32) tc_issue_loop<true, false>(p, my_tiles, tmem_base, umma_desc_lo(smem_u32(sA)), lay.stage_bytes, umma_desc_lo(smem_u32(sB)), 0, full_bar, empty_bar, tfull_bar, tempty_bar);
+        else tc_issue_loop<false, false>(p, my_tiles, tmem_base, umma_desc_lo(smem_u32(sA)), lay.stage_bytes, umma_desc_lo(smem_u32(sB)), 0, full_bar, empty_bar, tfull_bar, tempty_bar);
     } else if (warp < 4 || warp >= 8) {
         // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
         // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); they split the query columns.
         const uint32_t q4 = warp & 3;
-        const uint32_t col_split = (p.debug & 4u) ? p.N : ((p.N / 16 + 1) / 2) * 16;      // debug bit 2: first warp set takes every column
+        const uint32_t col_split = ((p.N / 16 + 1) / 2) * 16;
         const uint32_t col_begin = warp < 4 ? 0u : col_split, col_end = warp < 4 ? col_split : p.N;
         for (uint64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = t & 1;
@@ -345,18 +393,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // =====================================================================================================================
 // K2b — the same scan as tc_scan_kernel on CTA PAIRS (cta_group::2): two SMs of a TPC share one MMA of M = 256 rows.
-// Each CTA stages its own 128 rows of A and HALF of the query block per K-block (the tensor core reads B from both
-// CTAs' shared memory), so a stage costs 16 KB + N/2 x 128 B per CTA instead of keeping the whole query block
-// resident: up to 256 queries in ONE pass over HBM (config C3) and a much deeper TMA ring for small batches (C4).
+// Each CTA stages its own 128 rows of A and HALF of the query block per ring stage (the tensor core reads B from both
+// CTAs' shared memory), so a stage costs kbs x (16 KB + N/2 x 128 B) per CTA instead of keeping the whole query block
+// resident: up to 256 queries in ONE pass over HBM (config C3).
 // Leader CTA (cluster rank 0) issues the MMAs; both CTAs run a TMA producer whose transactions complete on the
 // LEADER's full barrier (peer bit of the barrier address cleared); tcgen05.commit multicasts the "stage free" and
 // "accumulator ready" arrivals to both CTAs; both CTAs' epilogue warps release the accumulator on the leader's
 // barrier (remote mbarrier.arrive through mapa).
 // =====================================================================================================================
-struct Tc2SmemLayout { uint32_t stage_bytes, off_bars, off_misc, off_thr, total; };
-__host__ __device__ inline Tc2SmemLayout tc2_smem_layout(uint32_t N, uint32_t stages) {
+struct Tc2SmemLayout { uint32_t a_bytes, stage_bytes, off_bars, off_misc, off_thr, total; };
+__host__ __device__ inline Tc2SmemLayout tc2_smem_layout(uint32_t N, uint32_t stages, uint32_t kbs) {
     Tc2SmemLayout L;
-    L.stage_bytes = kTcStageBytes + (N / 2) * 128;               // A tile + this CTA's half of the B K-block; multiple of 1024
+    L.a_bytes = kbs * kTcKBlockBytes;
+    L.stage_bytes = L.a_bytes + kbs * (N / 2) * 128;             // A tile + this CTA's half of the B K-blocks; multiple of 1024
     L.off_bars = stages * L.stage_bytes;
     L.off_misc = L.off_bars + (2 * stages + 4) * 8;
     L.off_thr = (L.off_misc + 16 + 15) & ~15u;
@@ -378,26 +427,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(pol)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, int c2, int c3, uint64_t* leader_bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(0), "r"(c2), "r"(c3), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on the same-offset barrier of cluster CTA `cta`
     asm volatile(
@@ -413,14 +453,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc2_raw[];
     uint8_t* smem = smem_tc2_raw + ((1024u - (smem_u32(smem_tc2_raw) & 1023u)) & 1023u);
-    const Tc2SmemLayout lay = tc2_smem_layout(p.N, p.stages);
+    const Tc2SmemLayout lay = tc2_smem_layout(p.N, p.stages, p.kbs);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tfull_bar = empty_bar + p.stages;    // [2]
     uint64_t* tempty_bar = tfull_bar + 2;          // [2] (leader's copy is the live one)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + lay.off_misc);
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -446,57 +486,43 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 4) {
-        // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
-            tma_prefetch_desc(&tmA);
-            tma_prefetch_desc(&tmB);
-            const uint64_t pol = l2_policy_evict_first();
-            uint64_t pol_keep;
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-            uint64_t it = 0;
-            for (uint64_t t = 0; t < my_tiles; ++t) {
-                const int row0 = (int)((first_tile + pair + t * npairs) * kPairRows + rank * kTcTileRows);
-                for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
-                    const uint32_t s = it % p.stages;
-                    if (it >= p.stages) mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
+        // ===================== TMA producer (both CTAs; warp-wide loop, one elected lane issues) =====================
+        const uint64_t pol = l2_policy_evict_first();
+        uint64_t pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        const int kbe = p.tf32 ? kTcKBlock / 2 : kTcKBlock;
+        if (elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+        __syncwarp();
+        uint32_t s = 0, ph = 1;
+        for (uint64_t t = 0; t < my_tiles; ++t) {
+            const int row0 = (int)((first_tile + pair + t * npairs) * kPairRows + rank * kTcTileRows);
+            for (uint32_t g = 0; g < p.groups; ++g) {
+                mbar_wait(&empty_bar[s], ph);
+                if (elect_one()) {
                     uint8_t* st = smem + (size_t)s * lay.stage_bytes;
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * lay.stage_bytes);     // both CTAs' bytes land on the leader
-                    const int kbe = p.tf32 ? kTcKBlock / 2 : kTcKBlock;
-                    tma_load_2d_2sm(st, &tmA, kb * kbe, row0, &full_bar[s], pol);
-                    tma_load_2d_2sm(st + kTcStageBytes, &tmB, kb * kbe, (int)(rank * half_n), &full_bar[s], pol_keep);
+                    if (p.box4d) {
+                        tma_load_4d_2sm(st, &tmA, (int)(g * p.kbs), row0 >> 3, &full_bar[s], pol);
+                        tma_load_4d_2sm(st + lay.a_bytes, &tmB, (int)(g * p.kbs), (int)((rank * half_n) >> 3), &full_bar[s], pol_keep);
+                    } else {
+                        tma_load_2d_2sm(st, &tmA, (int)g * kbe, row0, &full_bar[s], pol);
+                        tma_load_2d_2sm(st + lay.a_bytes, &tmB, (int)g * kbe, (int)(rank * half_n), &full_bar[s], pol_keep);
+                    }
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
-            const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kPairRows, p.N) : umma_idesc_f16(kPairRows, p.N);
-            uint64_t it = 0;
-            for (uint64_t t = 0; t < my_tiles; ++t) {
-                const uint32_t buf = t & 1;
-                mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * p.N;
-                for (uint32_t kb = 0; kb < p.nkb; ++kb, ++it) {
-                    const uint32_t s = it % p.stages;
-                    mbar_wait(&full_bar[s], (it / p.stages) & 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * lay.stage_bytes);
-                    const uint32_t b_addr = a_addr + kTcStageBytes;
-#pragma unroll
-                    for (uint32_t k = 0; k < kTcKBlock / 16; ++k) {
-                        if (p.tf32) umma_tf32_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
-                        else umma_f16_ss_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
-                    }
-                    umma_commit_2sm(&empty_bar[s]);
-                }
-                umma_commit_2sm(&tfull_bar[buf]);
-            }
+        // ===================== MMA issuer (leader CTA only; warp-wide loop, one elected lane issues) =====================
+        if (leader) {
+            if (p.tf32) tc_issue_loop<true, true>(p, my_tiles, tmem_base, umma_desc_lo(smem_u32(smem)), lay.stage_bytes, 0, lay.a_bytes, full_bar, empty_bar, tfull_bar, tempty_bar);
+            else tc_issue_loop<false, true>(p, my_tiles, tmem_base, umma_desc_lo(smem_u32(smem)), lay.stage_bytes, 0, lay.a_bytes, full_bar, empty_bar, tfull_bar, tempty_bar);
         }
     } else if (warp < 4 || warp >= 8) {
         // ===================== epilogue (both CTAs; each owns its 128 rows of the pair tile) =====================
         const uint32_t q4 = warp & 3;
-        const uint32_t col_split = (p.debug & 4u) ? p.N : ((p.N / 16 + 1) / 2) * 16;      // debug bit 2: first warp set takes every column
+        const uint32_t col_split = ((p.N / 16 + 1) / 2) * 16;
         const uint32_t col_begin = warp < 4 ? 0u : col_split, col_end = warp < 4 ? col_split : p.N;
         for (uint64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = t & 1;

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_kernel(const __grid_cons
                             const uint32_t b_addr = smem_u32(sB + (size_t)kb * p.N * 128);
 #pragma unroll
                             for (uint32_t k = 0; k < 4; ++k)
-                                umma_f16_ss(d_tmem, umma_desc_sw128_sbo(a_addr + k * 32, sbo), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                                umma_ss<false, false>(d_tmem, umma_desc_sw128_sbo(a_addr + k * 32, sbo), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
                         }
                     }
                     umma_commit(&empty[s]);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_kernel(const __grid_cons
             for (uint32_t c = 0; c < p.N; c += 16) {
                 uint32_t r[16];
                 tmem_ld_x16(taddr + c, r);
-                tmem_ld_wait();
+                tmem_ld_wait(r);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) sum += (long long)__uint_as_float(r[i]);
             }
