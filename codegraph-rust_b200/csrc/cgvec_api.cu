@@ -155,7 +155,7 @@ struct Index {
     std::vector<uint32_t> trace_kinds;      // 1 = scan, 2 = merge, 3 = exchange
     static constexpr uint32_t kTraceCap = 16384;
     int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 0, opt_tc_first = 0, opt_tc_kernel = 0, opt_tc_debug = 0, opt_tc2_max_n = kTc2MaxN;
-    int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0, opt_tc_kbs = 0;
+    int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0, opt_tc_kbs = 0, opt_tc_flow = 0;
     std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
 
     // stats
@@ -1144,6 +1144,7 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "tc_min_batch") ix->opt_tc_min_nq = (int)value;
     else if (k == "tc_stages") ix->opt_tc_stages = (int)value;
     else if (k == "tc_kbs") ix->opt_tc_kbs = (int)value;
+    else if (k == "tc_flow") ix->opt_tc_flow = (int)value;
     else if (k == "tc_max_n") ix->opt_tc_max_n = (int)value;
     else if (k == "tc_margin") ix->opt_tc_margin = (int)value;
     else if (k == "tc_target") ix->opt_tc_target = (int)value;

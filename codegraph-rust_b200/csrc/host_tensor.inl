@@ -56,7 +56,7 @@ bool tensor_path_applicable(const Index* ix, int metric, uint32_t nq) {
 // per ring stage and ring depth.  Measured (tools/tma_stream_bench.cu, profiles/r02_tma_stream_pipe.txt): one commit per
 // 16 KB K-block caps the ring at 5.2 TB/s whatever its depth, two or four K-blocks per stage reach 6.8-7.1 TB/s.
 struct TcPlan { bool pairs; uint32_t N, nkb, kbs, groups, stages, box4d, smem; };
-bool tc_plan_fill(const Index* ix, bool pairs, uint32_t N, TcPlan* out) {
+bool tc_plan_fill(const Index* ix, bool pairs, uint32_t N, TcPlan* out, uint32_t sel_cap = 2048) {
     const uint32_t kbe = ix->dtype == CGVEC_F32 ? kTcKBlock / 2 : kTcKBlock;
     const uint32_t nkb = (ix->dim + kbe - 1) / kbe;
     const bool can4d = ((size_t)ix->ld * ix->esize) % 128 == 0 && ix->opt_tc_kbs != 1 && nkb > 1;
@@ -69,7 +69,7 @@ bool tc_plan_fill(const Index* ix, bool pairs, uint32_t N, TcPlan* out) {
         uint32_t max_stages = ix->opt_tc_stages ? (uint32_t)ix->opt_tc_stages : (kbs >= 4 ? 3u : kbs >= 2 ? 6u : 12u);
         if (max_stages > kTcMaxStages) max_stages = kTcMaxStages;
         for (uint32_t s = max_stages; s >= min_stages; --s) {
-            const uint32_t total = (pairs ? tc2_smem_layout(N, s, kbs).total : tc_smem_layout(N, nkb, s, kbs).total) + 1024;
+            const uint32_t total = (pairs ? tc2_smem_layout(N, s, kbs, sel_cap).total : tc_smem_layout(N, nkb, s, kbs, sel_cap).total) + 1024;
             if (total <= kSmemBudget) {
                 out->pairs = pairs; out->N = N; out->nkb = nkb; out->kbs = kbs; out->groups = (nkb + kbs - 1) / kbs; out->stages = s;
                 out->box4d = kbs > 1 ? 1u : 0u; out->smem = total;
@@ -116,26 +116,28 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     if (n_max == 0 || nq > n_max) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u leaves no room for a resident query block", ix->dim);
     const uint32_t N = (nq + 15) & ~15u;
     const bool f32 = ix->dtype == CGVEC_F32;
-    TcPlan plan;
-    if (!tc_plan_fill(ix, pairs, N, &plan)) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the tensor kernel at N = %u, dimension %u", N, ix->dim);
-    const uint32_t kbe = f32 ? kTcKBlock / 2 : kTcKBlock;            // elements per 128-byte K-block
-    const uint32_t nkb = plan.nkb, dpad = nkb * kbe, stages = plan.stages;
-    const uint32_t tile_rows = pairs ? 2 * kTcTileRows : kTcTileRows;
     const uint64_t n = ix->n;
     const uint32_t want = (uint32_t)(k < n ? k : n);
     uint32_t kp = k + (ix->opt_tc_margin > 0 ? (uint32_t)ix->opt_tc_margin : (k / 2 > 32 ? k / 2 : 32));
     if (kp > kTcCap / 8) kp = kTcCap / 8;
     if (kp < k) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u is too large for the tensor path", k);
+    uint32_t sel_cap = next_pow2(kp + kTcSelStep);                    // selector sort buffer: best kp + at least one step of new keys
+    if (sel_cap < 512) sel_cap = 512;
+    TcPlan plan;
+    if (!tc_plan_fill(ix, pairs, N, &plan, sel_cap)) return fail(CGVEC_ERR_UNSUPPORTED, "no shared memory for the tensor kernel at N = %u, dimension %u", N, ix->dim);
+    const uint32_t kbe = f32 ? kTcKBlock / 2 : kTcKBlock;            // elements per 128-byte K-block
+    const uint32_t nkb = plan.nkb, dpad = nkb * kbe, stages = plan.stages;
+    const uint32_t tile_rows = pairs ? 2 * kTcTileRows : kTcTileRows;
 
     int rc;
     rc = ensure(&c->d_B, &c->B_cap, (size_t)N * dpad * (f32 ? 2 : 1)); if (rc) return rc;      // capacity counted in halves
     rc = ensure(&c->d_tc_f, &c->tcf_cap, (size_t)3 * kTc2MaxN); if (rc) return rc;
-    rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)2 * kTc2MaxN + 4); if (rc) return rc;
+    rc = ensure(&c->d_tc_u, &c->tcu_cap, (size_t)3 * kTc2MaxN + 4); if (rc) return rc;
     rc = ensure(&c->d_cand, &c->cand_cap, (size_t)kTc2MaxN * kTcCap); if (rc) return rc;
     rc = ensure(&c->d_exact, &c->exact_cap, (size_t)kTc2MaxN * (kTcCap / 8)); if (rc) return rc;
     rc = ensure(&c->h_proven, &c->hprov_cap, (size_t)kTc2MaxN + 4, true); if (rc) return rc;
     float *d_thr = c->d_tc_f, *d_na = c->d_tc_f + kTc2MaxN, *d_rho = c->d_tc_f + 2 * kTc2MaxN;
-    uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTc2MaxN, *d_overflow = c->d_tc_u + 2 * kTc2MaxN;
+    uint32_t *d_cnt = c->d_tc_u, *d_proven = c->d_tc_u + kTc2MaxN, *d_consumed = c->d_tc_u + 2 * kTc2MaxN, *d_overflow = c->d_tc_u + 3 * kTc2MaxN;
 
     if (f32) tc_prep_queries_kernel<float><<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, reinterpret_cast<float*>(c->d_B), d_na, d_rho, d_thr, d_cnt, d_overflow);
     else tc_prep_queries_kernel<__half><<<(N * 8 + 127) / 128, 128, 0, st>>>(d_q, qstride, nq, N, ix->dim, dpad, c->d_B, d_na, d_rho, d_thr, d_cnt, d_overflow);
@@ -159,37 +161,64 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     p.row_offset = map.row_offset; p.blk_rows = map.blk_rows; p.n_shards = map.n_shards; p.shard_id = map.shard_id;
     const uint32_t smem = plan.smem;
 
-    // geometric row ranges: after T rows the threshold sits at quantile kp/T, so a range of S rows adds about
-    // S*kp/T survivors; ranges are sized to keep each list near `target` entries (small sorts in tc_select_kernel)
-    // and never above cap (overflow -> exact-kernel fallback).
-    uint32_t target = ix->opt_tc_target > 0 ? (uint32_t)ix->opt_tc_target : 1024;
-    if (target < 4 * kp) target = 4 * kp;
-    if (target > kTcCap / 2) target = kTcCap / 2;
-    uint64_t T = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
-    while (T < n) {
-        uint64_t S = (T == 0) ? (ix->opt_tc_first > 0 ? (uint64_t)ix->opt_tc_first : target) : T * (target - kp) / kp;
-        if (T == 0 && S > kTcCap) S = kTcCap;
-        S = (S + tile_rows - 1) / tile_rows * tile_rows;
-        if (S < tile_rows) S = tile_rows;
-        if (T + S > n || (n - T - S) * 8 < S) S = n - T;      // fold a small remainder into this range
-        p.row_begin = T; p.row_end = T + S;
-        uint64_t tiles = (S + tile_rows - 1) / tile_rows;
+    p.kp = kp; p.sel_cap = sel_cap; p.consumed = d_consumed;
+    auto launch_range = [&](uint64_t begin, uint64_t end, uint32_t sel_on, uint32_t boot = 0) -> int {
+        p.row_begin = begin; p.row_end = end; p.sel_on = sel_on; p.boot = boot;
+        const uint64_t tiles = (end - begin + tile_rows - 1) / tile_rows;
         if (pairs) {
             const uint64_t max_pairs = (uint64_t)ix->sm_count / 2;
-            uint32_t grid = 2 * (uint32_t)(tiles < max_pairs ? tiles : max_pairs);
+            const uint32_t grid = 2 * (uint32_t)(tiles < max_pairs ? tiles : max_pairs);
             tc2_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
         } else {
-            uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
+            const uint32_t grid = (uint32_t)(tiles < (uint64_t)ix->sm_count ? tiles : (uint64_t)ix->sm_count);
             tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
         }
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
-        tc_select_kernel<<<nq, 1024, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_thr, kTcCap, kp, kTcCap);
+        return CGVEC_OK;
+    };
+    auto launch_select = [&](uint32_t mode, uint32_t fixed_cnt = 0) -> int {
+        tc_select_kernel<<<nq, 1024, kTcCap * 8, st>>>(c->d_cand, d_cnt, d_consumed, d_thr, kTcCap, kp, kTcCap, mode, fixed_cnt);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
-        T += S;
+        return CGVEC_OK;
+    };
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
+    if (ix->opt_tc_flow == 0) {
+        // Bootstrap range (every row survives: thresholds are -inf) -> select -> ONE launch over the rest of the shard whose
+        // selector warps keep tightening the thresholds in place -> select.  Unwritten list slots must read as 0.
+        CUDA_TRY(cudaMemsetAsync(c->d_cand, 0, (size_t)nq * kTcCap * sizeof(uint64_t), st));
+        uint64_t S0 = ix->opt_tc_first > 0 ? (uint64_t)ix->opt_tc_first : 4096;
+        if (S0 > kTcCap) S0 = kTcCap;
+        S0 = (S0 + tile_rows - 1) / tile_rows * tile_rows;
+        if (S0 >= n || (n - S0) * 4 < S0) S0 = n;                         // a small shard is one range
+        if (S0 > kTcCap) {                                                // (remainder folded in: fall back to fixed ranges of <= cap rows)
+            S0 = kTcCap / tile_rows * tile_rows;
+        }
+        rc = launch_range(0, S0, 0, 1); if (rc) return rc;
+        rc = launch_select(S0 >= n ? 2u : 0u, (uint32_t)S0); if (rc) return rc;
+        if (S0 < n) {
+            rc = launch_range(S0, n, 1); if (rc) return rc;
+            rc = launch_select(1); if (rc) return rc;
+        }
+    } else {
+        // legacy flow (option tc_flow = 1, kept for A/B timing): geometrically growing row ranges with a select in between.
+        // After T rows the threshold sits at quantile kp/T, so a range of S rows adds about S*kp/T survivors per query.
+        uint32_t target = ix->opt_tc_target > 0 ? (uint32_t)ix->opt_tc_target : 1024;
+        if (target < 4 * kp) target = 4 * kp;
+        if (target > kTcCap / 2) target = kTcCap / 2;
+        uint64_t T = 0;
+        while (T < n) {
+            uint64_t S = (T == 0) ? (ix->opt_tc_first > 0 ? (uint64_t)ix->opt_tc_first : target) : T * (target - kp) / kp;
+            if (T == 0 && S > kTcCap) S = kTcCap;
+            S = (S + tile_rows - 1) / tile_rows * tile_rows;
+            if (S < tile_rows) S = tile_rows;
+            if (T + S > n || (n - T - S) * 8 < S) S = n - T;      // fold a small remainder into this range
+            rc = launch_range(T, T + S, 0); if (rc) return rc;
+            rc = launch_select(2); if (rc) return rc;
+            T += S;
+        }
     }
     if (ix->opt_timing) {
         CUDA_TRY(cudaEventRecord(e1, st));

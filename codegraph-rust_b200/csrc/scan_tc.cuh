@@ -41,11 +41,16 @@ struct TcParams {
     uint64_t n_rows;            // local rows of the shard (rows >= n_rows are TMA zero fill and masked)
     uint64_t row_begin, row_end;   // this launch scans local rows [row_begin, row_end); row_begin % 256 == 0
     const float* norms;         // squared row norms (reference order); cosine only
-    const float* thr;           // [N] per-query thresholds in dot/|row| units
-    uint64_t* cand;             // [N][cap] candidate keys
+    float* thr;                 // [N] per-query thresholds in dot/|row| units (tightened in place by the selector warps)
+    uint64_t* cand;             // [N][cap] candidate keys: [0, kp) = the query's current best (sorted), [kp, count) = appended survivors
     uint32_t* cand_count;       // [N]
+    uint32_t* consumed;         // [N] appended entries below this index are already folded into the best list
     uint32_t* overflow;         // set when a list would exceed cap
     uint32_t cap;
+    uint32_t kp;                // survivors kept per query (k + margin)
+    uint32_t sel_on;            // 1: warps 6-7 of every CTA refresh thresholds while the scan runs (main range); 0: thresholds fixed
+    uint32_t boot;              // 1: bootstrap range: EVERY score is kept, stored at cand[q][row - row_begin] (no thresholds, no atomics)
+    uint32_t sel_cap;           // keys in the selector's sort buffer (power of two, >= 2 * kp)
     uint32_t nq;                // real queries (<= N)
     uint32_t N;                 // MMA N: nq rounded up to 16
     uint32_t nkb;               // 128-byte K-blocks per row: ceil(d / 64) halves or ceil(d / 32) floats
@@ -62,8 +67,8 @@ struct TcParams {
 };
 
 // Shared-memory plan of tc_scan_kernel: resident query block | ring of row stages | barriers | misc | thresholds
-struct TcSmemLayout { uint32_t off_b, off_a, stage_bytes, off_bars, off_misc, off_thr, total; };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(uint32_t N, uint32_t nkb, uint32_t stages, uint32_t kbs) {
+struct TcSmemLayout { uint32_t off_b, off_a, stage_bytes, off_bars, off_misc, off_thr, off_sel, total; };
+__host__ __device__ inline TcSmemLayout tc_smem_layout(uint32_t N, uint32_t nkb, uint32_t stages, uint32_t kbs, uint32_t sel_cap) {
     TcSmemLayout L;
     L.off_b = 0;
     L.off_a = nkb * N * 128;                                   // multiple of 1024 because N % 8 == 0
@@ -71,7 +76,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(uint32_t N, uint32_t nkb,
     L.off_bars = L.off_a + stages * L.stage_bytes;
     L.off_misc = L.off_bars + (2 * stages + 1 + 4) * 8;        // tmem base address
     L.off_thr = (L.off_misc + 16 + 15) & ~15u;                 // negated thresholds, 16-byte aligned for LDS.128
-    L.total = L.off_thr + N * 4;
+    L.off_sel = L.off_thr + N * 4;                             // selector sort buffer
+    L.total = L.off_sel + 2 * sel_cap * 8;                     // one buffer per selector warp
     return L;
 }
 
@@ -178,10 +184,21 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
 // register buffers that are indexed statically (a dynamically indexed buffer would live in local memory: the
 // first version of this epilogue spent a quarter of the kernel in STL/LDL round trips).  Fast path per column: one FFMA
 // (acc * 1/|row| - thr, thresholds pre-negated in shared memory, LDS.128) and a share of a 3-input AND of sign bits; a
-// single ballot per 16 columns decides whether ANY lane has a survivor.  Only then (rare once thresholds have
-// tightened) the slow path reserves list slots with warp-aggregated atomics and writes the keys.
+// single ballot per 16 columns decides whether ANY lane has a survivor.  Slow path (rare once thresholds have
+// tightened): the surviving lane reserves a list slot with one atomicAdd and PARKS the key; the store that needs the
+// atomic's result is issued at the lane's next survivor or at the end of the tile, so no warp ever waits out the
+// atomic's round trip to L2 (that wait, ~1 us per slow path, was what kept the C3 epilogue from hiding behind the MMAs).
+struct TcPending { uint32_t q, pos; uint64_t key; };
+constexpr uint32_t kTcNoPending = 0xffffffffu;
+__device__ __forceinline__ void tc_flush_pending(const TcParams& p, TcPending& pd) {
+    if (pd.q != kTcNoPending) {
+        if (pd.pos < p.cap) p.cand[(size_t)pd.q * p.cap + pd.pos] = pd.key;
+        else *p.overflow = 1u;
+        pd.q = kTcNoPending;
+    }
+}
 __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint32_t (&r)[16], const float* __restrict__ s_nthr, uint32_t c0,
-                                                  uint64_t row, bool valid, float inv, uint32_t lane) {
+                                                  uint32_t grow, uint32_t boot_slot, bool valid, float inv, TcPending& pd) {
     float t[16];
     uint32_t all_neg = 0x80000000u;                                   // sign bit survives iff every t[j] is negative
 #pragma unroll
@@ -194,52 +211,168 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
         all_neg &= __float_as_uint(t[4 * j4 + 0]) & __float_as_uint(t[4 * j4 + 1]);
         all_neg &= __float_as_uint(t[4 * j4 + 2]) & __float_as_uint(t[4 * j4 + 3]);
     }
+    if (p.boot) {                                                     // bootstrap range: slot = row, one coalesced store per column
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j)
+            if (boot_slot < p.cap && c0 + j < p.nq)
+                p.cand[(size_t)(c0 + j) * p.cap + boot_slot] = valid ? make_key(__uint_as_float(r[j]) * inv, grow, false) : 0ull;
+        return;
+    }
     const bool maybe = valid && !(all_neg & 0x80000000u);
     if (__ballot_sync(0xffffffffu, maybe) == 0u) return;
-    // ---- slow path: reserve slots for all 16 columns first (independent atomics in flight), then write
-    uint32_t masks[16], base[16];
+    if (maybe) {
 #pragma unroll
-    for (uint32_t j = 0; j < 16; ++j) {
-        masks[j] = __ballot_sync(0xffffffffu, valid && t[j] >= 0.0f);
-        base[j] = 0;
-        if (masks[j] && (int)lane == __ffs(masks[j]) - 1) base[j] = atomicAdd(&p.cand_count[c0 + j], (uint32_t)__popc(masks[j]));
-    }
-    const uint64_t b = row / p.blk_rows, rr = row - b * p.blk_rows;
-    const uint32_t g = (uint32_t)((b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);
-#pragma unroll
-    for (uint32_t j = 0; j < 16; ++j) {
-        if (masks[j]) {
-            const uint32_t bj = __shfl_sync(0xffffffffu, base[j], __ffs(masks[j]) - 1);
-            if (masks[j] & (1u << lane)) {
-                const uint32_t pos = bj + __popc(masks[j] & ((1u << lane) - 1));
-                if (pos < p.cap) p.cand[(size_t)(c0 + j) * p.cap + pos] = make_key(__uint_as_float(r[j]) * inv, g, false);
-                else *p.overflow = 1u;
+        for (uint32_t j = 0; j < 16; ++j) {
+            if (t[j] >= 0.0f) {
+                tc_flush_pending(p, pd);
+                pd.q = c0 + j;
+                pd.key = make_key(__uint_as_float(r[j]) * inv, grow, false);
+                pd.pos = atomicAdd(&p.cand_count[c0 + j], 1u);
             }
         }
     }
+    __syncwarp();
 }
 
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t taddr, const float* __restrict__ s_nthr, uint64_t row,
-                                                 bool valid, float inv, uint32_t lane, uint32_t col_begin, uint32_t col_end) {
+                                                 bool valid, float inv, uint32_t col_begin, uint32_t col_end) {
     if ((p.debug & 2u) || col_begin >= col_end) return;
+    const uint64_t b = row / p.blk_rows, rr = row - b * p.blk_rows;
+    const uint32_t grow = (uint32_t)((b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);   // global row of this lane
+    const uint32_t boot_slot = (uint32_t)(row - p.row_begin);
+    TcPending pd;
+    pd.q = kTcNoPending; pd.pos = 0; pd.key = 0;
     uint32_t ra[16], rb[16];
     tmem_ld_x16(taddr + col_begin, ra);
     for (uint32_t c0 = col_begin; c0 < col_end; c0 += 32) {
         tmem_ld_wait(ra);
         const bool more = c0 + 16 < col_end;
         if (more) tmem_ld_x16(taddr + c0 + 16, rb);                       // next 16 columns stream in behind the compares
-        tc_epilogue_chunk(p, ra, s_nthr, c0, row, valid, inv, lane);
+        tc_epilogue_chunk(p, ra, s_nthr, c0, grow, boot_slot, valid, inv, pd);
         if (more) {
             tmem_ld_wait(rb);
             if (c0 + 32 < col_end) tmem_ld_x16(taddr + c0 + 32, ra);
-            tc_epilogue_chunk(p, rb, s_nthr, c0 + 16, row, valid, inv, lane);
+            tc_epilogue_chunk(p, rb, s_nthr, c0 + 16, grow, boot_slot, valid, inv, pd);
         }
     }
+    tc_flush_pending(p, pd);
 }
 
 // Negated thresholds of this launch -> shared memory (padding columns get -inf so they can never survive).
 __device__ __forceinline__ void tc_stage_thresholds(const TcParams& p, float* s_nthr, uint32_t tid, uint32_t nthreads) {
     for (uint32_t j = tid; j < p.N; j += nthreads) s_nthr[j] = j < p.nq ? -p.thr[j] : __int_as_float(0xff800000);
+}
+
+// ---- selector (warp 7 of every CTA, main range only) ------------------------------------------------------------------
+// Tightens the per-query thresholds WHILE the scan runs, so one launch covers the whole shard (the first version
+// relaunched the scan six times with a sort kernel in between).  Query q belongs to CTA q mod gridDim.  Its list is
+// cand[q]: [0, kp) the best kp approximate keys seen so far (sorted, owned by the selector), [kp, count) survivors
+// appended by every CTA's epilogue.  A round of the selector folds the newly appended keys [consumed, ...) into the best
+// list with a warp-wide bitonic sort in shared memory and publishes the kp-th best as the new threshold; all selectors
+// copy the thresholds of ALL queries into their CTA's shared memory once per round.  A slot whose key is still 0 has been
+// reserved (atomicAdd) but not written yet: the round stops in front of it.  Any threshold ever published is the kp-th
+// best of a subset of the rows seen, hence <= the final kp-th best: the true top-kp by approximate score always survive,
+// which is all the exact re-score + proof that follow need.
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_volatile_f32(const float* ptr) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_f32(float* ptr, float v) { asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(ptr), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ptr)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* s, uint32_t n, uint32_t lane) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = lane; i < (n >> 1); i += 32) {
+                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = s[lo], b = s[hi];
+                if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+constexpr uint32_t kTcEpilogueWarps = 8;
+constexpr uint32_t kTcSelStep = 256;              // appended keys examined per step of a selector round (8 loads in flight per lane)
+__device__ __noinline__ void tc_selector_loop(const TcParams& p, uint64_t* s_sort, const uint32_t* s_epi_done, uint32_t sel, uint32_t nsel,
+                                              uint32_t lane) {
+    const uint32_t kp = p.kp, new_max = p.sel_cap - kp;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    while (lds_volatile_u32(s_epi_done) < kTcEpilogueWarps) {
+        for (uint32_t q = sel; q < p.nq; q += nsel) {
+            const uint32_t cons = __ldcg(p.consumed + q);
+            uint32_t cnt = ld_volatile_u32(p.cand_count + q);
+            if (cnt > p.cap) cnt = p.cap;
+            if (cnt <= cons) continue;
+            uint64_t* c = p.cand + (size_t)q * p.cap;
+            // Appended keys were admitted under whatever threshold their CTA had at the time; only those above the CURRENT
+            // kp-th best can change the best list.  Filtering is one compare per key, so a backlog built up under a loose
+            // early threshold is worked off at L2-read speed and only the few keys that matter reach the sort.
+            const uint64_t kth_cur = __ldcg(c + kp - 1);
+            uint32_t pos = cons, nb = 0;
+            bool blocked = false;                                         // ran into a reserved-but-unwritten slot
+            while (!blocked && pos < cnt && nb + kTcSelStep <= new_max) {
+                uint64_t key[kTcSelStep / 32];
+#pragma unroll
+                for (uint32_t u = 0; u < kTcSelStep / 32; ++u) {
+                    const uint32_t i = pos + u * 32 + lane;
+                    key[u] = i < cnt ? __ldcg(c + i) : 0ull;
+                }
+                uint32_t examined = 0;
+#pragma unroll
+                for (uint32_t u = 0; u < kTcSelStep / 32; ++u) {
+                    if (blocked) break;
+                    const uint32_t i = pos + u * 32 + lane;
+                    const bool inr = i < cnt;
+                    const uint32_t unwritten = __ballot_sync(0xffffffffu, inr && key[u] == 0ull);
+                    uint32_t span = min(32u, cnt > pos + u * 32 ? cnt - (pos + u * 32) : 0u);
+                    if (unwritten) { span = __ffs(unwritten) - 1; blocked = true; }
+                    const bool pass = lane < span && key[u] > kth_cur;
+                    const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                    if (pass) s_sort[kp + nb + __popc(mask & lt_mask)] = key[u];
+                    nb += __popc(mask);
+                    examined += span;
+                }
+                pos += examined;
+            }
+            if (pos == cons) continue;
+            if (nb) {
+                for (uint32_t i = lane; i < kp; i += 32) s_sort[i] = __ldcg(c + i);
+                uint32_t n = 2;
+                while (n < kp + nb) n <<= 1;
+                for (uint32_t i = kp + nb + lane; i < n; i += 32) s_sort[i] = 0ull;
+                __syncwarp();
+                warp_bitonic_sort_desc(s_sort, n, lane);
+                for (uint32_t i = lane; i < kp; i += 32) __stcg(c + i, s_sort[i]);
+            }
+            if (lane == 0) {
+                __stcg(p.consumed + q, pos);
+                if (nb) {
+                    const uint64_t kth = s_sort[kp - 1];
+                    if (kth != 0ull) st_volatile_f32(p.thr + q, key_score(kth, false));
+                }
+            }
+            __syncwarp();
+            if (lds_volatile_u32(s_epi_done) >= kTcEpilogueWarps) return;
+        }
+    }
+}
+// Epilogue warps re-read their columns' thresholds from global memory once per tile (behind the accumulator wait), so a
+// threshold published by any selector takes effect everywhere within one tile time.
+__device__ __forceinline__ void tc_refresh_thresholds(const TcParams& p, float* s_nthr, uint32_t col_begin, uint32_t col_end, uint32_t lane) {
+    for (uint32_t j = col_begin + lane; j < col_end; j += 32)
+        if (j < p.nq) s_nthr[j] = -ld_volatile_f32(p.thr + j);
+    __syncwarp();
 }
 
 // ---- MMA issue loop (one elected thread) ------------------------------------------------------------------------------
@@ -299,7 +432,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window; the launch reserves 1 KB of slack for this
     uint8_t* smem = smem_tc_raw + ((1024u - (smem_u32(smem_tc_raw) & 1023u)) & 1023u);
-    const TcSmemLayout lay = tc_smem_layout(p.N, p.nkb, p.stages, p.kbs);
+    const TcSmemLayout lay = tc_smem_layout(p.N, p.nkb, p.stages, p.kbs, p.sel_cap);
     uint8_t* sB = smem + lay.off_b;
     uint8_t* sA = smem + lay.off_a;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
@@ -314,7 +447,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint64_t num_tiles = (p.row_end - p.row_begin + kTcTileRows - 1) / kTcTileRows;
     const uint64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
+    uint32_t* s_epi_done = s_tmem + 1;
+    uint64_t* s_sort = reinterpret_cast<uint64_t*>(smem + lay.off_sel);
     if (tid == 0) {
+        *s_epi_done = 0;
         for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(b_bar, 1);
         mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
@@ -378,13 +514,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float nb = valid ? p.norms[row] : 0.0f;
                 inv = nb > 0.0f ? rsqrtf(nb) : 0.0f;                     // zero-norm row -> cosine 0 (simd_ops.rs:73-74)
             }
+            if (p.sel_on) tc_refresh_thresholds(p, s_nthr, col_begin, col_end, lane);
             mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
             tc_fence_after();
-            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, lane, col_begin, col_end);
+            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, col_begin, col_end);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
+        if (lane == 0) atomicAdd(s_epi_done, 1u);
+    } else if (p.sel_on) {                                           // warps 6 and 7: selectors
+        tc_selector_loop(p, s_sort + (size_t)(warp - 6) * p.sel_cap, s_epi_done, 2 * blockIdx.x + (warp - 6), 2 * gridDim.x, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -401,15 +541,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // "accumulator ready" arrivals to both CTAs; both CTAs' epilogue warps release the accumulator on the leader's
 // barrier (remote mbarrier.arrive through mapa).
 // =====================================================================================================================
-struct Tc2SmemLayout { uint32_t a_bytes, stage_bytes, off_bars, off_misc, off_thr, total; };
-__host__ __device__ inline Tc2SmemLayout tc2_smem_layout(uint32_t N, uint32_t stages, uint32_t kbs) {
+struct Tc2SmemLayout { uint32_t a_bytes, stage_bytes, off_bars, off_misc, off_thr, off_sel, total; };
+__host__ __device__ inline Tc2SmemLayout tc2_smem_layout(uint32_t N, uint32_t stages, uint32_t kbs, uint32_t sel_cap) {
     Tc2SmemLayout L;
     L.a_bytes = kbs * kTcKBlockBytes;
     L.stage_bytes = L.a_bytes + kbs * (N / 2) * 128;             // A tile + this CTA's half of the B K-blocks; multiple of 1024
     L.off_bars = stages * L.stage_bytes;
     L.off_misc = L.off_bars + (2 * stages + 4) * 8;
     L.off_thr = (L.off_misc + 16 + 15) & ~15u;
-    L.total = L.off_thr + N * 4;
+    L.off_sel = L.off_thr + N * 4;
+    L.total = L.off_sel + 2 * sel_cap * 8;                     // one buffer per selector warp
     return L;
 }
 
@@ -453,7 +594,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc2_raw[];
     uint8_t* smem = smem_tc2_raw + ((1024u - (smem_u32(smem_tc2_raw) & 1023u)) & 1023u);
-    const Tc2SmemLayout lay = tc2_smem_layout(p.N, p.stages, p.kbs);
+    const Tc2SmemLayout lay = tc2_smem_layout(p.N, p.stages, p.kbs, p.sel_cap);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tfull_bar = empty_bar + p.stages;    // [2]
@@ -470,7 +611,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint64_t my_tiles = (num_tiles > pair) ? (num_tiles - pair + npairs - 1) / npairs : 0;
     const uint32_t half_n = p.N >> 1;
 
+    uint32_t* s_epi_done = s_tmem + 1;
+    uint64_t* s_sort = reinterpret_cast<uint64_t*>(smem + lay.off_sel);
     if (tid == 0) {
+        *s_epi_done = 0;
         for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
         mbar_init(&tempty_bar[0], 16); mbar_init(&tempty_bar[1], 16);
@@ -533,9 +677,10 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const float nb = valid ? p.norms[row] : 0.0f;
                 inv = nb > 0.0f ? rsqrtf(nb) : 0.0f;
             }
+            if (p.sel_on) tc_refresh_thresholds(p, s_nthr, col_begin, col_end, lane);
             mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
             tc_fence_after();
-            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, lane, col_begin, col_end);
+            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, col_begin, col_end);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -543,6 +688,9 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 else mbar_arrive_cta(&tempty_bar[buf], 0);
             }
         }
+        if (lane == 0) atomicAdd(s_epi_done, 1u);
+    } else if (p.sel_on) {                                           // warps 6 and 7: selectors
+        tc_selector_loop(p, s_sort + (size_t)(warp - 6) * p.sel_cap, s_epi_done, 2 * blockIdx.x + (warp - 6), 2 * gridDim.x, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -550,26 +698,49 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 6) tmem_dealloc_2sm(tmem_base, p.tmem_cols);
 }
 
-// ---- between row ranges: keep each query's best kp candidates, publish the new threshold ---------------------
-// grid = nq, block = 1024, dynamic smem = sort_cap * 8.  cand[q][0..count) -> sorted best kp in cand[q][0..kp).
+// ---- per-query selection around the scan launches: keep each query's best kp candidates, publish the threshold --------
+// grid = nq, block = 1024, dynamic smem = sort_cap * 8.
+//   mode 0 (after the bootstrap range, before the main range): cand[q][0..count) -> sorted best kp in [0, kp) (0-padded),
+//          [kp, count) cleared, count = consumed = kp: the main range appends behind the best list.
+//   mode 1 (after the main range): [0, kp) U [consumed, count) -> sorted best kp in [0, kp), count = live keys among them.
+//   mode 2 (the bootstrap range was the whole shard): like mode 0 but count = live keys.
 __global__ void __launch_bounds__(1024) tc_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count,
-                                                         float* __restrict__ thr, uint32_t cap, uint32_t kp, uint32_t sort_cap) {
+                                                         uint32_t* __restrict__ consumed, float* __restrict__ thr, uint32_t cap,
+                                                         uint32_t kp, uint32_t sort_cap, uint32_t mode, uint32_t fixed_cnt) {
     extern __shared__ __align__(16) uint64_t s_sel_keys[];
+    __shared__ uint32_t s_live;
     uint64_t* s_keys = s_sel_keys;
     const uint32_t q = blockIdx.x;
-    uint32_t cnt = cand_count[q];
+    uint32_t cnt = fixed_cnt ? fixed_cnt : cand_count[q];             // bootstrap range: one slot per row, no counter
     if (cnt > cap) cnt = cap;
+    uint32_t cons = 0, total = cnt;
+    if (mode == 1) {
+        cons = consumed[q];
+        if (cons < kp) cons = kp;
+        if (cons > cnt) cons = cnt;
+        total = (cnt >= kp) ? kp + (cnt - cons) : cnt;
+    }
     uint32_t n = 2;
-    while (n < cnt) n <<= 1;
+    while (n < total) n <<= 1;
     if (n > sort_cap) n = sort_cap;
     uint64_t* c = cand + (size_t)q * cap;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = (i < cnt) ? c[i] : 0ull;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint64_t key = 0ull;
+        if (i < total) key = (mode == 1 && i >= kp) ? c[cons + (i - kp)] : c[i];
+        s_keys[i] = key;
+    }
+    if (threadIdx.x == 0) s_live = 0;
     __syncthreads();
     bitonic_sort_desc(s_keys, n, threadIdx.x, blockDim.x, 0);
-    const uint32_t keep = cnt < kp ? cnt : kp;
+    for (uint32_t i = threadIdx.x; i < kp && i < n; i += blockDim.x)
+        if (s_keys[i] != 0ull && (i + 1 == kp || i + 1 == n || s_keys[i + 1] == 0ull)) s_live = i + 1;
+    __syncthreads();
+    const uint32_t keep = s_live;
     for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) c[i] = (i < keep) ? s_keys[i] : 0ull;
+    if (mode == 0) for (uint32_t i = kp + threadIdx.x; i < cnt; i += blockDim.x) c[i] = 0ull;
     if (threadIdx.x == 0) {
-        cand_count[q] = keep;
+        cand_count[q] = (mode == 0) ? kp : keep;
+        if (mode == 0) consumed[q] = kp;
         thr[q] = (keep >= kp) ? key_score(s_keys[kp - 1], false) : __int_as_float(0xff800000);   // -inf until kp found
     }
 }
