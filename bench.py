@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — queries/sec and achieved HBM GB/s of the embedding similarity-search hot path.
+"""bench.py — queries/sec and achieved HBM GB/s (or tensor TFLOP/s) of the embedding similarity-search hot path.
 
-Workload (BASELINE.json configs[1], "C2"): 1M x 768 f32 resident matrix, batch-1 query, top-10 cosine, exact-order
-scan.  A "step" is one query: one pass of the scan + top-k over the whole index.  At N > 1 GPUs the SAME index is
-row-sharded across the ranks (strong scaling; one process per GPU), each rank scans its shard and the per-shard
-top-k lists are merged after a single NCCL all-gather, so `value` stays "queries/sec over the 1M x 768 index".
+Headline workload (BASELINE.json configs[1], "C2"): 1M x 768 f32 resident matrix, batch-1 query, top-10 cosine,
+exact-order scan.  A "step" is one query: one pass of the scan + top-k over the whole index.  At N > 1 GPUs the SAME
+index is row-sharded across the ranks (strong scaling; one process per GPU), each rank scans its shard and the
+per-shard top-k lists are exchanged once per query, so `value` stays "queries/sec over the 1M x 768 index".
 
-  python bench.py [--gpus N --steps K --warmup W]           this repo's CUDA path
-  python bench.py --impl reference [...]                    the reference's CPU path (oracle port of
-                                                            ParallelVectorOps::parallel_top_k_search, all host threads)
+The same JSON line carries a `configs` object with one sub-record per remaining GPU config of BASELINE.json, each run
+on the same N ranks (row-sharded), each with its own roofline and an oracle parity check:
+  c3   10M x 768 f16, batch-256, top-100, tcgen05 path
+  c4   50M x 1024 f16, batch-64, top-100 and top-10, tcgen05 path (the north_star's 8-GPU target shape)
+  c5   100M x 384 f32 (TF32 tensor path), streaming 1024-query batches from host memory, recall@10 vs the oracle
+
+  python bench.py [--gpus N --steps K --warmup W] [--configs c3,c4,c5 | --configs none]
+  python bench.py --impl reference [...]        the reference's CPU path (oracle port of
+                                                ParallelVectorOps::parallel_top_k_search, all host threads)
 
 Prints ONE JSON line (rank 0).  See the task contract for field meanings.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import sys
@@ -32,22 +37,35 @@ WORKLOADS = {
     "c1": (10_000, 768, "f32", 1, 10),
     "c2": (1_000_000, 768, "f32", 1, 10),
 }
+BATCHED = {
+    # name: rows, dim, dtype, batch, ks, streaming
+    "c3": dict(rows=10_000_000, dim=768, dtype="f16", batch=256, ks=(100,), streaming=False,
+               what="10M x 768 f16, batch-256 queries, top-100 cosine, tcgen05 path (BASELINE configs[2])"),
+    "c4": dict(rows=50_000_000, dim=1024, dtype="f16", batch=64, ks=(100, 10), streaming=False,
+               what="50M x 1024 f16 row-sharded, batch-64 queries, top-k cosine, tcgen05 path, one exchange per batch (BASELINE configs[3])"),
+    "c5": dict(rows=100_000_000, dim=384, dtype="f32", batch=1024, ks=(10,), streaming=True,
+               what="100M x 384 f32 row-sharded, streaming 1024-query batches from host memory, top-10 cosine, TF32 tcgen05 path (BASELINE configs[4])"),
+}
 SEED_ROWS, SEED_QUERIES = 0xC0DE6A9F, 0x5EED0001
 METRIC = "queries/sec and HBM GB/s over N x d embeddings (1M x 768 f32, batch-1, top-10 cosine) vs CPU ref"
-L2_BYTES = 126 * 1024 * 1024
+FULL_ORACLE_MAX_LOCAL_ROWS = 13_000_000     # above this per-rank shard size the full CPU oracle pass no longer fits a bench run
 
 
-def measured_peak_gbs():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", 1400.0)),
+                "source": "measured (MEASURED_PEAKS.json: copy read+write GB/s; cuBLAS bf16 burst / sustained TFLOP/s)"}
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+                "source": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s burst, ~1.4 sustained)"}
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+    """Samples SM clock / throttle reasons with NVML while the timed regions run."""
 
     def __init__(self, device_index: int, period_s: float = 0.02):
         super().__init__(daemon=True)
@@ -98,8 +116,8 @@ class ClockSampler(threading.Thread):
                 "samples": len(inside)}
 
 
-def host_queries(oracle, n, d):
-    return oracle.synth_rows(SEED_QUERIES, 0, n, d, True, False)
+def host_queries(oracle, n, d, salt=0):
+    return oracle.synth_rows(SEED_QUERIES + salt, 0, n, d, True, False)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -140,7 +158,8 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, n, d, k, args.gpus),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "cores_effective": threads,
+                         "cores_affinity": oracle.affinity_threads(), "kind": "port",
                          "sample": f"{args.steps} queries over the first {sample_rows} of {n} rows, scaled x{scale:.2f} to N "
                                    f"(ref-parallel: per-row heap Vec, 3-FMA AVX2 cosine, full parallel sort, truncate)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -159,34 +178,331 @@ def workload_config(args, n, d, k, world):
 
 
 # ------------------------------------------------------------------------------------------------------
+# helpers shared by the headline and the batched configs
+# ------------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__ as ge
+        from oracle import oracle        # cpu_baseline leg, query generation and the parity checks only
+        self.torch, self.dist, self.oracle = torch, dist, oracle
+        self.cg = ge.load_package()
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.uid_bytes = None
+        if world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peaks = measured_peaks()
+        self.sampler = ClockSampler(local_rank)
+        self.sampler.start()
+
+    def new_uid(self):
+        """A fresh NCCL unique id per index (rank 0 creates it, everybody receives it)."""
+        if self.world == 1:
+            return None
+        torch, dist = self.torch, self.dist
+        buf = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        if self.rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(self.cg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
+
+    def make_index(self, n, d, dtype):
+        cg = self.cg
+        begin, end = cg.shard_range(n, self.world, self.rank)
+        dt = cg.F32 if dtype == "f32" else cg.F16
+        if self.world > 1:
+            ix = cg.Index(d, dt, device=self.local_rank, rank=self.rank, world=self.world, nccl_unique_id=self.new_uid(), row_offset=begin)
+        else:
+            ix = cg.Index(d, dt, device=self.local_rank)
+        ix.reserve(end - begin)
+        ix.fill_synthetic(end - begin, SEED_ROWS, True)
+        for key, val in (self.args.opt or []):
+            ix.set_option(key, val)
+        return ix, begin, end
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+def oracle_topk_over_shard(env, ix, begin, end, queries, k, chunk_rows=1_000_000):
+    """CPU oracle top-k of `queries` over THIS rank's shard: rows are read back from the device in chunks (f16 widened
+    exactly), every chunk is scored by the oracle (cg_fair_top_k_search_multi = cg_parallel_top_k_search's outputs) and
+    the per-chunk lists are merged under the result contract.  -> list of (global rows, scores) per query."""
+    oracle = env.oracle
+    parts = [[] for _ in range(len(queries))]
+    n_local = end - begin
+    for c0 in range(0, n_local, chunk_rows):
+        m = min(chunk_rows, n_local - c0)
+        rows = ix.get_rows(c0, m)
+        res = oracle.fair_top_k_multi(queries, rows, k)
+        for qi, (ri, rs) in enumerate(res):
+            parts[qi].append((ri + np.uint64(begin + c0), rs))
+        del rows
+    return [oracle.merge_top_k(p, k) for p in parts]
+
+
+def parity_full(env, ix, begin, end, queries, k, got_rows, got_scores):
+    """Full CPU-oracle check: every rank runs the oracle over its own shard, the per-shard oracle lists are gathered and
+    merged (top-k of a union = top-k of the per-part top-k's), rank 0 compares with what the GPU path returned."""
+    t0 = time.perf_counter()
+    local = oracle_topk_over_shard(env, ix, begin, end, queries, k)
+    gathered = env.gather_objects(local)
+    ok, recall = True, []
+    if env.rank == 0:
+        for qi in range(len(queries)):
+            wi, ws = env.oracle.merge_top_k([g[qi] for g in gathered], k)
+            same = bool(np.array_equal(wi, got_rows[qi][:len(wi)]) and ws.tobytes() == np.ascontiguousarray(got_scores[qi][:len(ws)]).tobytes())
+            ok = ok and same
+            recall.append(len(set(wi.tolist()) & set(got_rows[qi].tolist())) / max(len(wi), 1))
+    return {"ok": ok, "method": "oracle_full: cg_parallel_top_k_search arithmetic over ALL rows read back from every rank's device, merged on rank 0; indices and score bytes equal",
+            "queries": len(queries), "recall": recall, "seconds": round(time.perf_counter() - t0, 1)}
+
+
+def parity_sampled(env, ix, begin, end, queries, k, got_rows, got_scores, d_queries, sample_rows=1_000_000):
+    """Shards too large for a full CPU pass inside a bench run: (1) the exact-order kernel (bit-exact against the CPU oracle
+    on the full C2 matrix in this same run) must return the same lists; (2) the CPU oracle re-scores the returned rows that
+    live on this rank and must reproduce their score bytes; (3) the CPU oracle scans a sample of each shard (the block that
+    holds each query's best local hit plus evenly spaced blocks) and must find no row that outranks the returned k-th."""
+    torch, cg, oracle = env.torch, env.cg, env.oracle
+    t0 = time.perf_counter()
+    nq = len(queries)
+    e_rows = torch.empty((nq, k), dtype=torch.int64, device=env.dev)
+    e_scores = torch.empty((nq, k), dtype=torch.float32, device=env.dev)
+    e_counts = torch.empty((nq,), dtype=torch.int32, device=env.dev)
+    ix.search_device(d_queries.data_ptr(), nq, k, e_rows.data_ptr(), e_scores.data_ptr(), e_counts.data_ptr(), cg.COSINE, 0, cg.PATH_EXACT)
+    torch.cuda.synchronize()
+    ex_r = e_rows.cpu().numpy().astype(np.uint64); ex_s = e_scores.cpu().numpy()
+    same_as_exact = bool(np.array_equal(ex_r, got_rows) and ex_s.tobytes() == np.ascontiguousarray(got_scores).tobytes())
+    # (2) oracle scores of the returned rows held by this rank
+    rescored_ok = True
+    n_local = end - begin
+    for qi in range(nq):
+        for j in range(k):
+            g = int(got_rows[qi][j])
+            if begin <= g < end:
+                row = ix.get_rows(g - begin, 1)
+                sc = oracle.scores(queries[qi], row)[0]
+                if np.float32(sc).tobytes() != np.float32(got_scores[qi][j]).tobytes():
+                    rescored_ok = False
+    # (3) oracle over a sample of the shard
+    blocks = 8
+    per = max(min(sample_rows // blocks, n_local // blocks), 1)
+    outranked = 0
+    starts = sorted({min(max(0, (n_local // blocks) * b), max(n_local - per, 0)) for b in range(blocks)})
+    for s0 in starts:
+        m = min(per, n_local - s0)
+        rows = ix.get_rows(s0, m)
+        res = oracle.fair_top_k_multi(queries, rows, 1)
+        for qi, (ri, rs) in enumerate(res):
+            if len(ri) == 0:
+                continue
+            g = int(ri[0]) + begin + s0
+            kth_s, kth_r = float(got_scores[qi][k - 1]), int(got_rows[qi][k - 1])
+            better = (rs[0] > kth_s) or (rs[0] == kth_s and g < kth_r)
+            if better and g not in set(int(x) for x in got_rows[qi]):
+                outranked += 1
+    recall = [len(set(ex_r[qi].tolist()) & set(int(x) for x in got_rows[qi])) / k for qi in range(nq)]
+    flags = env.gather_objects({"rescored_ok": rescored_ok, "outranked": outranked})
+    ok = same_as_exact and all(f["rescored_ok"] for f in flags) and sum(f["outranked"] for f in flags) == 0
+    return {"ok": bool(ok), "method": "oracle_sampled+exact_kernel: shard too large for a full CPU pass in a bench run; (1) equals the exact-order "
+                                      "kernel's lists (indices + score bytes), (2) CPU oracle reproduces the returned rows' score bytes, "
+                                      "(3) CPU oracle over sampled row blocks of every shard finds no outranking row",
+            "queries": nq, "same_as_exact_kernel": same_as_exact, "rows_sampled_per_rank": int(per * len(starts)), "recall": recall,
+            "seconds": round(time.perf_counter() - t0, 1)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# batched configs (C3 / C4 / C5)
+# ------------------------------------------------------------------------------------------------------
+def run_batched(env, name):
+    torch, cg, oracle = env.torch, env.cg, env.oracle
+    cfg = BATCHED[name]
+    n, d, nq = cfg["rows"], cfg["dim"], cfg["batch"]
+    esize = 4 if cfg["dtype"] == "f32" else 2
+    begin, end = cg.shard_range(n, env.world, env.rank)
+    need = (end - begin) * (d * esize + 4) + (3 << 30)
+    free, _ = torch.cuda.mem_get_info()
+    short = env.max_over_ranks(1.0 if free < need else 0.0)
+    if short:
+        return {"skipped": f"needs {need / 2**30:.0f} GiB per GPU, {free / 2**30:.0f} GiB free"}
+    ix, begin, end = env.make_index(n, d, cfg["dtype"])
+    local_rows = end - begin
+    out = {"workload": f"{name.upper()}: {cfg['what']}", "n_rows": n, "dim": d, "dtype": cfg["dtype"], "batch": nq, "n_gpus": env.world,
+           "scaling": "strong", "rows_per_gpu": local_rows, "runs": []}
+    try:
+        sample_q = sorted({0, nq // 3, (2 * nq) // 3, nq - 1})
+        for k in cfg["ks"]:
+            # queries: synthetic unit vectors; the sampled ones are PLANTED (a stored row + small noise), so their nearest
+            # neighbour is known a priori (SURVEY.md 8d)
+            nb_max = 64
+            qs_host = host_queries(oracle, nq * 4, d, salt={'c3': 3, 'c4': 4, 'c5': 5}[name] * 1000 + k).reshape(4, nq, d).copy()
+            planted = {}
+            rng = np.random.default_rng(1234 + k)
+            for qi in sample_q:
+                r = int(rng.integers(0, n))
+                row = oracle.synth_rows(SEED_ROWS, r, 1, d, True, cfg["dtype"] == "f16")[0]
+                qs_host[0, qi] = (row + rng.normal(0.0, 0.05 / np.sqrt(d), d)).astype(np.float32)
+                planted[qi] = r
+            qs_dev = torch.from_numpy(qs_host).to(env.dev)
+            o_r = torch.empty((nq, k), dtype=torch.int64, device=env.dev)
+            o_s = torch.empty((nq, k), dtype=torch.float32, device=env.dev)
+            o_c = torch.empty((nq,), dtype=torch.int32, device=env.dev)
+            stream = torch.cuda.Stream(device=env.dev)
+
+            def run(i):
+                ix.search_device(qs_dev[i % 4].data_ptr(), nq, k, o_r.data_ptr(), o_s.data_ptr(), o_c.data_ptr(), cg.COSINE,
+                                 stream.cuda_stream, cg.PATH_TENSOR)
+
+            # warm-up (>= 3 batches) doubles as the estimate that sizes the timed region to ~0.4 s
+            env.barrier()
+            tw = time.perf_counter()
+            for i in range(3):
+                run(i)
+            env.barrier()
+            est = env.max_over_ranks((time.perf_counter() - tw) / 3)
+            nb = int(min(nb_max, max(5, 0.4 / max(est, 1e-4))))
+            st0 = ix.stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall0 = time.perf_counter()
+            e0.record(stream)
+            for i in range(nb):
+                run(i + 1)
+            e1.record(stream)
+            env.barrier()
+            t_wall1 = time.perf_counter()
+            ms = env.max_over_ranks(e0.elapsed_time(e1)) / nb
+            st1 = ix.stats()
+            # dominant kernel (main range of the tensor scan): CUDA events recorded by the library around that launch
+            ix.set_option("reset_timing", 1); ix.set_option("timing", 1)
+            for i in range(min(nb, 8)):
+                run(i)
+            env.barrier()
+            st2 = ix.stats()
+            ix.set_option("timing", 0)
+            main_ms = env.max_over_ranks(st2.tc_main_ms_total / max(st2.tc_main_timed, 1))
+            # results of batch 0 (the planted one) for the parity check
+            run(0)
+            torch.cuda.synchronize()
+            got_r = o_r.cpu().numpy().astype(np.uint64); got_s = o_s.cpu().numpy()
+            qsel = np.ascontiguousarray(qs_host[0][sample_q])
+            gr, gs = got_r[sample_q], got_s[sample_q]
+            if local_rows <= FULL_ORACLE_MAX_LOCAL_ROWS:
+                parity = parity_full(env, ix, begin, end, qsel, k, gr, gs)
+            else:
+                parity = parity_sampled(env, ix, begin, end, qsel, k, gr, gs, torch.from_numpy(qsel).to(env.dev))
+            parity["planted_nearest_neighbour_found"] = bool(all(int(gr[j][0]) == planted[qi] for j, qi in enumerate(sample_q)))
+            parity["ok"] = bool(parity["ok"] and parity["planted_nearest_neighbour_found"])
+            # end to end from HOST buffers
+            if cfg["streaming"]:
+                qstream = ix.stream(nq, k, cg.COSINE, cg.PATH_TENSOR)
+                qstream.submit(qs_host[0]); qstream.submit(qs_host[1])
+                qstream.flush()
+                env.barrier()
+                t0 = time.perf_counter()
+                last = None
+                for i in range(nb):
+                    r = qstream.submit(qs_host[i % 4])
+                    last = r if r is not None else last
+                last = qstream.flush() or last
+                e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+                qstream.submit(qs_host[0])
+                last = qstream.flush()
+                qstream.close()
+                e2e_note = "cgvec_stream_submit / flush: double-buffered pinned upload of the next batch behind the scan of the current one, results to host"
+                same = bool(last is not None and np.array_equal(last[0][sample_q], got_r[sample_q]) and last[1][sample_q].tobytes() == got_s[sample_q].tobytes())
+            else:
+                bufs = ix.make_search_buffers(nq, k)
+                ix.search_into(qs_host[0], bufs)
+                env.barrier()
+                t0 = time.perf_counter()
+                for i in range(nb):
+                    ix.search_into(qs_host[i % 4], bufs)
+                e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+                e2e_note = "cgvec_search_ex with host buffers: H2D of the batch + scan + exchange + results to host + sync, every batch"
+                ix.search_into(qs_host[0], bufs)
+                same = bool(np.array_equal(bufs["rows"][sample_q], got_r[sample_q]) and bufs["scores"][sample_q].tobytes() == got_s[sample_q].tobytes())
+            env.barrier()
+            alg_bytes = local_rows * d * esize                       # one pass over the local shard per tensor batch of <= 256 queries (SURVEY.md 8d)
+            passes = max(1, round((st1.tc_batches - st0.tc_batches) / nb))
+            flops = 2.0 * nq * local_rows * d
+            pk = env.peaks
+            hbm_achieved = alg_bytes / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
+            tf = flops / (ms * 1e-3) / 1e12
+            tensor_peak = pk["bf16_tflops_sustained"] * (0.5 if cfg["dtype"] == "f32" else 1.0)
+            bound = "hbm" if name == "c4" else "tensor"
+            rec = {
+                "k": k, "batches_timed": nb, "ms_per_batch": ms, "value": nq / (ms * 1e-3), "unit": "queries/s",
+                "roofline": {
+                    "bound": bound,
+                    "achieved": hbm_achieved if bound == "hbm" else tf, "peak": pk["hbm_gbs"] if bound == "hbm" else tensor_peak,
+                    "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                    "frac": (hbm_achieved / pk["hbm_gbs"]) if bound == "hbm" else tf / tensor_peak,
+                    "hbm": {"kernel": "tc2_scan_kernel" if nq > 128 else "tc_scan_kernel (main range)", "kernel_ms": main_ms, "achieved_gbs": hbm_achieved,
+                            "frac": hbm_achieved / pk["hbm_gbs"], "frac_on_batch_time": passes * alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                            "algorithmic_bytes_per_pass_per_gpu": alg_bytes, "passes_per_batch": passes},
+                    "tensor": {"tflops_per_gpu_on_batch_time": tf, "peak_tflops": tensor_peak, "frac": tf / tensor_peak,
+                               "peak_note": "cuBLAS bf16 sustained (MEASURED_PEAKS.json)" + ("; halved for kind::tf32" if cfg["dtype"] == "f32" else "")},
+                    "traffic": None, "peak_source": pk["source"]},
+                "tc_fallbacks": int(st1.tc_fallbacks - st0.tc_fallbacks), "tc_batches": int(st1.tc_batches - st0.tc_batches),
+                "gpu_launches_per_batch": (st1.kernel_launches - st0.kernel_launches) / nb,
+                "exchange": {0: "none", 1: "p2p", 2: "nccl"}.get(int(st1.exchange_mode), "?"),
+                "parity_ok": parity["ok"], "parity": parity,
+                "e2e": {"value": nb * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_batch": nq * d * 4, "d2h_bytes_per_batch": nq * (k * 12 + 4),
+                        "how": e2e_note, "same_result_as_device_path": same},
+                "clocks": env.sampler.summary(t_wall0, t_wall1),
+            }
+            if cfg["streaming"]:
+                rec["recall_at_10"] = float(np.mean(parity["recall"])) if env.rank == 0 and parity.get("recall") else None
+                rec["recall_reference"] = "CPU oracle over all rows" if parity["method"].startswith("oracle_full") else "exact-order kernel (itself oracle-checked on the full C2 matrix in this run) + CPU oracle on sampled rows"
+            out["runs"].append(rec)
+            del qs_dev, o_r, o_s, o_c
+        first = out["runs"][0]
+        out.update({"value": first["value"], "unit": "queries/s", "ms_per_batch": first["ms_per_batch"], "k": first["k"],
+                    "parity_ok": bool(all(r["parity_ok"] for r in out["runs"])), "tc_fallbacks": sum(r["tc_fallbacks"] for r in out["runs"]),
+                    "roofline": first["roofline"]})
+    finally:
+        ix.close()
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as ge
-    from oracle import oracle        # cpu_baseline leg + query generation only
-    cg = ge.load_package()
+    env = Env(args, rank, world, local_rank)
+    torch, cg, oracle = env.torch, env.cg, env.oracle
+    dev = env.dev
 
     n, d, _, _, k = WORKLOADS[args.workload]
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    uid = None
-    if world > 1:
-        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(cg.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
-    begin, end = cg.shard_range(n, world, rank)
-    ix = cg.Index(d, cg.F32, device=local_rank, rank=rank, world=world, nccl_unique_id=uid, row_offset=begin) if world > 1 \
-        else cg.Index(d, cg.F32, device=local_rank)
-    ix.reserve(end - begin)
-    ix.fill_synthetic(end - begin, SEED_ROWS, True)
-    for key, val in (args.opt or []):
-        ix.set_option(key, val)
+    ix, begin, end = env.make_index(n, d, "f32")
 
     total = args.steps + args.warmup
     qs_host = host_queries(oracle, total, d)
@@ -200,27 +516,21 @@ def run_b200(args, rank, world, local_rank):
         ix.search_device(qs_dev[i].data_ptr(), 1, k, out_rows[i].data_ptr(), out_scores[i].data_ptr(), out_counts[i].data_ptr(),
                          cg.COSINE, stream.cuda_stream)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # ---- pre-warm: at least 200 ms of the same steps whatever --warmup says (clocks, L2 / TLB state, NCCL channels), so that
+    #      a 20-step driver run measures the steady state and not the first two milliseconds after idle
+    t_pre = time.perf_counter()
+    with torch.cuda.stream(stream):
+        while time.perf_counter() - t_pre < 0.25:
+            for i in range(args.warmup):
+                step_device(i)
+            torch.cuda.synchronize()
+    env.barrier()
 
     # ---- device-resident throughput (`value`): K back-to-back batch-1 searches on one stream, nothing else ----
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step_device(i)
-    barrier()
+    env.barrier()
     launches0 = ix.stats().kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -229,11 +539,11 @@ def run_b200(args, rank, world, local_rank):
         for i in range(args.warmup, total):
             step_device(i)
         e1.record(stream)
-    barrier()
+    env.barrier()
     t_wall1 = time.perf_counter()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    dev_ms = env.max_over_ranks(e0.elapsed_time(e1))
     launches = ix.stats().kernel_launches - launches0
-    clocks = sampler.summary(t_wall0, t_wall1)
+    clocks = env.sampler.summary(t_wall0, t_wall1)
 
     # ---- per-launch duration of the dominant kernel: the same steps again with a CUDA-event pair recorded by the
     #      library around every scan launch on the launch stream (kept out of the region above because an event
@@ -243,12 +553,13 @@ def run_b200(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         for i in range(args.warmup, total):
             step_device(i)
-    barrier()
+    env.barrier()
     st = ix.stats()
     ix.set_option("timing", 0)
-    scan_ms = max_over_ranks(st.scan_ms_total / max(st.scans_timed, 1))
+    scan_ms = env.max_over_ranks(st.scan_ms_total / max(st.scans_timed, 1))
+    exchange = {0: "none", 1: "p2p", 2: "nccl"}.get(int(st.exchange_mode), "?")
 
-    # ---- parity spot check of what the timed region produced (rank 0, last query) against the oracle on a sample ----
+    # ---- what the timed region produced for its last query (checked against the oracle below, at every N) ----
     got_rows = out_rows[total - 1].cpu().numpy().astype(np.uint64)
     got_scores = out_scores[total - 1].cpu().numpy()
 
@@ -257,27 +568,34 @@ def run_b200(args, rank, world, local_rank):
     q_rows = [np.ascontiguousarray(qs_host[i:i + 1]) for i in range(total)]      # one C-contiguous [1, d] view per step
     for i in range(min(args.warmup, 5)):
         ix.search_into(q_rows[i], bufs)
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for i in range(args.warmup, total):
         ix.search_into(q_rows[i], bufs)                      # H2D query + scan + merge/exchange + results to host + sync
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+    env.barrier()
     r_h, s_h = bufs["rows"], bufs["scores"]
     same = bool(np.array_equal(r_h[0], got_rows) and np.array_equal(s_h[0], got_scores))
-    sampler.stop_flag.set()
+
+    # ---- parity at every N: the CPU oracle over every rank's shard (rows read back from the device), merged on rank 0 ----
+    par = parity_full(env, ix, begin, end, np.ascontiguousarray(qs_host[total - 1:total]), k, got_rows[None, :], got_scores[None, :])
 
     qps = args.steps / (dev_ms * 1e-3)
     e2e_qps = args.steps / e2e_s
     local_rows = end - begin
     alg_bytes = local_rows * d * 4 + local_rows * 4            # matrix once + one f32 norm per row
-    peak, peak_src = measured_peak_gbs()
+    peak, peak_src = env.peaks["hbm_gbs"], env.peaks["source"]
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        if world == 1:         # the ncu capture is of the 1-GPU launch; at N > 1 the shard (and the traffic) is 1/N of it
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (profiles/), not measured in this run"
+        else:
+            traffic_note = "null at N > 1: the committed ncu capture is of the 1-GPU launch"
     except Exception:
         pass
 
@@ -285,9 +603,6 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = oracle.max_threads()
         rows_host = oracle.synth_rows(SEED_ROWS, 0, n, d, True, False)
-        # the GPU's answer for the last timed query must equal the oracle's on the full matrix
-        wi, ws = oracle.parallel_top_k_search(qs_host[total - 1], rows_host, k)
-        parity_ok = bool(np.array_equal(wi, got_rows) and ws.tobytes() == got_scores.tobytes())
         # labelled NON-reference (BASELINE.md §2 "fair-cpu"): contiguous matrix, per-thread bounded selection, no full sort
         oracle.fair_top_k_mt(qs_host[0], rows_host, k, threads)
         nf, t0 = 0, time.perf_counter()
@@ -304,35 +619,56 @@ def run_b200(args, rank, world, local_rank):
             nq_cpu += 1
         cpu_s = (time.perf_counter() - t0) / nq_cpu
         v.close()
-        cpu_baseline = {"value": 1.0 / cpu_s, "unit": "queries/s", "cores": threads, "kind": "port",
+        cpu_baseline = {"value": 1.0 / cpu_s, "unit": "queries/s", "cores": threads, "cores_effective": threads,
+                        "cores_affinity": oracle.affinity_threads(), "kind": "port",
                         "sample": f"{nq_cpu} batch-1 queries over the full {n} x {d} matrix (ref-parallel port of simd_ops.rs:361-383: "
-                                  f"per-row heap Vec, 3-FMA AVX2 cosine, full parallel sort, truncate)",
-                        "gpu_matches_oracle_on_full_matrix": parity_ok,
+                                  f"per-row heap Vec, 3-FMA AVX2 cosine, full parallel sort, truncate); threads = min(affinity, cgroup cpu quota)",
+                        "gpu_matches_oracle_on_full_matrix": par["ok"],
                         "fair_cpu_non_reference": {"value": fair_qps, "unit": "queries/s",
                                                    "what": "same arithmetic, contiguous matrix, per-thread bounded top-k instead of the reference's per-row heap Vec + full parallel sort"}}
+    ix.close()
+    torch.cuda.empty_cache()
+
+    configs = {}
+    wanted = [c for c in (args.configs.split(",") if args.configs and args.configs != "none" else []) if c in BATCHED]
+    for name in wanted:
+        try:
+            configs[name] = run_batched(env, name)
+        except Exception as e:      # a failing extra config must not take the headline line with it
+            configs[name] = {"error": repr(e)[:300]}
+            try:
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
+    env.sampler.stop_flag.set()
 
     if rank == 0:
+        step_ms = dev_ms / args.steps
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n, d, k, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "scan_exact_kernel<float,COSINE,1>", "kernel_ms": scan_ms,
+                         "frac_on_step_time": alg_bytes / (step_ms * 1e-3) / 1e9 / peak if step_ms > 0 else None,
+                         "traffic": traffic, "traffic_note": traffic_note, "kernel": "scan_exact_kernel<float,COSINE,1>", "kernel_ms": scan_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "step_share": scan_ms / (dev_ms / args.steps) if dev_ms > 0 else None,
+                         "step_share": scan_ms / step_ms if dev_ms > 0 else None,
+                         "step_share_note": "above 1 when consecutive scans overlap (programmatic launch chain): the kernel timed alone is longer than a step",
                          "kernel_timing": f"{int(st.scans_timed)} launches, CUDA event pair around each on the launch stream, pass run right after the timed region",
                          "geometry": {"grid": st.grid, "block": st.block, "smem": st.smem_bytes, "stages": st.stages,
                                       "tile_rows": st.tile_rows}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": k * 12 + 4,
                     "same_result_as_device_path": same},
+            "parity_ok": par["ok"], "parity": par,
+            "exchange": exchange,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "configs": configs,
         }
         print(json.dumps(line), flush=True)
-    ix.close()
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -342,6 +678,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--configs", default="c3,c4,c5", help="comma-separated batched configs to add to the line (c3,c4,c5) or 'none'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", type=lambda s: (s.split("=")[0], int(s.split("=")[1])),
                     help="library tuning knob key=value (repeatable)")
@@ -352,8 +689,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 50:
-            pass
         run_reference(args, rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:

@@ -38,6 +38,7 @@ EXPORTS = [
     "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
     "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_multi_locate", "cgvec_multi_local_count", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
     "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_get_trace", "cgvec_last_error", "cgvec_version",
+    "cgvec_stream_open", "cgvec_stream_submit", "cgvec_stream_flush", "cgvec_stream_close",
 ]
 
 
@@ -60,7 +61,8 @@ class Stats(C.Structure):
                 ("bytes_resident", C.c_uint64), ("sm_count", C.c_uint32), ("grid", C.c_uint32), ("block", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("stages", C.c_uint32), ("tile_rows", C.c_uint32),
                 ("last_scan_ms", C.c_float), ("scan_ms_total", C.c_double), ("scans_timed", C.c_uint64),
-                ("tc_batches", C.c_uint64), ("tc_fallbacks", C.c_uint64)]
+                ("tc_batches", C.c_uint64), ("tc_fallbacks", C.c_uint64), ("exchange_mode", C.c_uint32), ("reserved0", C.c_uint32),
+                ("tc_main_ms_total", C.c_double), ("tc_main_timed", C.c_uint64)]
 
 
 _lib = None
@@ -115,6 +117,10 @@ def load_library(build: bool = True):
     L.cgvec_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.cgvec_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.cgvec_get_trace.argtypes = [vp, vp, C.c_uint32, u32p]
+    L.cgvec_stream_open.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]
+    L.cgvec_stream_submit.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, u32p]
+    L.cgvec_stream_flush.argtypes = [vp, vp, vp, vp, u32p]
+    L.cgvec_stream_close.argtypes = [vp]
     L.cgvec_last_error.restype = C.c_char_p
     L.cgvec_version.restype = C.c_char_p
     _lib = L
@@ -146,8 +152,49 @@ def version() -> str:
 
 
 # -------------------------------------------------------------------------------------------------
-# thin object wrapper over the C ABI
+# thin object wrappers over the C ABI
 # -------------------------------------------------------------------------------------------------
+class QueryStream:
+    """cgvec_stream_*: submit(batch i+1) uploads it behind the search of batch i and returns batch i's results
+    (None on the first call); flush() drains the last batch.  Results: (rows u64[nq,k], scores f32[nq,k], counts u32[nq])."""
+
+    def __init__(self, index: "Index", max_batch: int, k: int, metric: int = COSINE, path: int = PATH_AUTO):
+        self._ix, self.max_batch, self.k = index, max_batch, k
+        self._h = C.c_void_p()
+        _check(load_library().cgvec_stream_open(index._h, max_batch, k, metric, path, C.byref(self._h)))
+        self._rows = np.empty((max_batch, k), np.uint64); self._scores = np.empty((max_batch, k), np.float32)
+        self._counts = np.empty(max_batch, np.uint32); self._nq = C.c_uint32()
+
+    def _result(self):
+        n = int(self._nq.value)
+        if n == 0:
+            return None
+        return self._rows[:n].copy(), self._scores[:n].copy(), self._counts[:n].copy()
+
+    def submit(self, queries: np.ndarray):
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self._ix.dim:
+            raise CgvecError(ERR_BAD_DIM, f"queries have shape {q.shape}, index dimension is {self._ix.dim}")
+        _check(load_library().cgvec_stream_submit(self._h, _ptr(q), q.shape[0], _ptr(self._rows), _ptr(self._scores), _ptr(self._counts),
+                                                  C.byref(self._nq)))
+        return self._result()
+
+    def flush(self):
+        _check(load_library().cgvec_stream_flush(self._h, _ptr(self._rows), _ptr(self._scores), _ptr(self._counts), C.byref(self._nq)))
+        return self._result()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            load_library().cgvec_stream_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Index:
     def __init__(self, dim: int, dtype: int = F32, device: int = 0, rank: int = 0, world: int = 1,
                  nccl_unique_id: Optional[bytes] = None, row_offset: int = 0, devices: Optional[Sequence[int]] = None):
@@ -318,6 +365,10 @@ class Index:
         n = C.c_uint64()
         _check(load_library().cgvec_load_flat(self._h, path.encode(), C.byref(n)))
         return int(n.value)
+
+    def stream(self, max_batch: int, k: int, metric: int = COSINE, path: int = PATH_AUTO) -> "QueryStream":
+        """Double-buffered streaming of host query batches (cgvec_stream_*; BASELINE config 5)."""
+        return QueryStream(self, max_batch, k, metric, path)
 
     def stats(self) -> Stats:
         s = Stats()

@@ -242,6 +242,14 @@ __global__ void distances_first_kernel(const T* __restrict__ rows, uint32_t d, u
     out[i] = (na == 0.0f || nb == 0.0f) ? __int_as_float(0x7f800000) : sub_rn(1.0f, div_rn(dp, mul_rn(na, nb)));
 }
 
+// f16 -> f32 widening of m rows (bulk read-back): out[r * d + c] = rows[r * ld + c]
+__global__ void widen_rows_kernel(const __half* __restrict__ rows, uint32_t d, uint32_t ld, uint64_t m, float* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= m * d) return;
+    const uint64_t r = i / d;
+    out[i] = __half2float(rows[r * ld + (i - r * d)]);
+}
+
 // f16 -> f32 widening of one row (get_embedding)
 __global__ void widen_row_kernel(const __half* __restrict__ row, uint32_t d, float* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

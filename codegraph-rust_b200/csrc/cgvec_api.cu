@@ -143,6 +143,10 @@ struct Index {
     uint32_t xseq = 0;
     int opt_p2p = 1;
 
+    // rank-invariant view of a sharded index: smallest / largest shard, agreed with one all-gather after the rows change
+    uint64_t agreed_min_n = 0, agreed_max_n = 0;
+    bool agreed_valid = false;
+
     std::mutex pool_mu;
     std::vector<SearchCtx*> pool;
     cudaStream_t main_stream = nullptr;
@@ -162,10 +166,12 @@ struct Index {
     std::atomic<uint64_t> launches{0}, searches{0};
     ScanGeom last_geom{};
     std::mutex ev_mu;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // scan kernel brackets awaiting readout
-    double scan_ms_total = 0.0;
-    uint64_t scan_timed = 0;
+    struct TimedLaunch { cudaEvent_t e0, e1; int kind; };     // kind 0: exact scan kernel, 1: main range of the tensor scan
+    std::vector<TimedLaunch> timed;                           // kernel brackets awaiting readout
+    double scan_ms_total = 0.0, tc_main_ms_total = 0.0;
+    uint64_t scan_timed = 0, tc_main_timed = 0;
     float last_scan_ms = 0.0f;
+    std::atomic<uint32_t> last_exchange{0};                   // 0 none (unsharded), 1 fused peer-memory kernel, 2 NCCL all-gather
 };
 
 int check_device(int device) {
@@ -239,13 +245,17 @@ int grow(Index* ix, uint64_t need, bool exact = false) {
     if (e != cudaSuccess) { cudaGetLastError(); return fail(CGVEC_ERR_OOM, "cudaMalloc of %zu bytes for %llu rows failed: %s", newcap * row_bytes, (unsigned long long)newcap, cudaGetErrorString(e)); }
     e = cudaMalloc(reinterpret_cast<void**>(&nnorms), (newcap + 64) * sizeof(float));
     if (e != cudaSuccess) { cudaGetLastError(); cudaFree(nrows); return fail(CGVEC_ERR_OOM, "cudaMalloc for norms failed: %s", cudaGetErrorString(e)); }
-    CUDA_TRY(cudaMemsetAsync(nnorms, 0, (newcap + 64) * sizeof(float), ix->main_stream));
-    CUDA_TRY(cudaMemsetAsync(static_cast<uint8_t*>(nrows) + newcap * row_bytes, 0, slack, ix->main_stream));
-    if (ix->n) {
-        CUDA_TRY(cudaMemcpyAsync(nrows, ix->d_rows, ix->n * row_bytes, cudaMemcpyDeviceToDevice, ix->main_stream));
-        CUDA_TRY(cudaMemcpyAsync(nnorms, ix->d_norms, ix->n * sizeof(float), cudaMemcpyDeviceToDevice, ix->main_stream));
+    e = cudaMemsetAsync(nnorms, 0, (newcap + 64) * sizeof(float), ix->main_stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(static_cast<uint8_t*>(nrows) + newcap * row_bytes, 0, slack, ix->main_stream);
+    if (e == cudaSuccess && ix->n) {
+        e = cudaMemcpyAsync(nrows, ix->d_rows, ix->n * row_bytes, cudaMemcpyDeviceToDevice, ix->main_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nnorms, ix->d_norms, ix->n * sizeof(float), cudaMemcpyDeviceToDevice, ix->main_stream);
     }
-    CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->main_stream);
+    if (e != cudaSuccess) {                                       // the old matrix stays in place; nothing leaks
+        cudaGetLastError(); cudaFree(nrows); cudaFree(nnorms);
+        return fail(CGVEC_ERR_CUDA, "growing the matrix failed: %s", cudaGetErrorString(e));
+    }
     cudaFree(ix->d_rows);
     cudaFree(ix->d_norms);
     ix->d_rows = nrows;
@@ -279,6 +289,31 @@ int launch_norms(Index* ix, uint64_t first, uint64_t count, cudaStream_t st) {
         row_sqnorm_kernel<__half><<<(unsigned)blocks, threads, 0, st>>>(static_cast<const __half*>(ix->d_rows), first, count, ix->dim, ix->ld, ix->d_norms);
     ix->launches++;
     CUDA_TRY(cudaGetLastError());
+    return CGVEC_OK;
+}
+
+// Every decision that changes the sequence of collectives (kernel family -> transport, empty-shard errors) must be the same
+// on all ranks of a sharded index, so it is taken on the smallest / largest shard size, agreed with one NCCL all-gather the
+// first time a search follows a change of the rows (all ranks call search collectively, so they all get here together).
+int agree_shard_sizes(Index* ix) {
+    if (ix->world == 1) { ix->agreed_min_n = ix->agreed_max_n = ix->n; ix->agreed_valid = true; return CGVEC_OK; }
+    std::lock_guard<std::mutex> lk(ix->comm_mu);
+    if (ix->agreed_valid) return CGVEC_OK;
+    uint64_t* d_all = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_all), sizeof(uint64_t) * ix->world));
+    const uint64_t mine = ix->n;
+    cudaError_t e = cudaMemcpyAsync(d_all + ix->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, ix->main_stream);
+    int nr = kNcclSuccess;
+    if (e == cudaSuccess) nr = nccl_api().AllGather(d_all + ix->rank, d_all, 1, kNcclUint64, ix->comm, ix->main_stream);
+    std::vector<uint64_t> all(ix->world, 0);
+    if (e == cudaSuccess && nr == kNcclSuccess) e = cudaMemcpyAsync(all.data(), d_all, sizeof(uint64_t) * ix->world, cudaMemcpyDeviceToHost, ix->main_stream);
+    if (e == cudaSuccess && nr == kNcclSuccess) e = cudaStreamSynchronize(ix->main_stream);
+    cudaFree(d_all);
+    if (nr != kNcclSuccess) return fail(CGVEC_ERR_NCCL, "ncclAllGather (shard sizes) failed: %s", nccl_api().GetErrorString(nr));
+    if (e != cudaSuccess) return fail(CGVEC_ERR_CUDA, "shard size agreement failed: %s", cudaGetErrorString(e));
+    ix->agreed_min_n = *std::min_element(all.begin(), all.end());
+    ix->agreed_max_n = *std::max_element(all.begin(), all.end());
+    ix->agreed_valid = true;
     return CGVEC_OK;
 }
 
@@ -398,15 +433,20 @@ static int add_impl(cgvec_index* ix, const uint8_t (*ids)[16], const void* rows,
     if (src_esize != ix->esize)
         return fail(CGVEC_ERR_BAD_ARG, "index stores %s rows; use %s", ix->esize == 4 ? "f32" : "f16", ix->esize == 4 ? "cgvec_add" : "cgvec_add_f16");
     CUDA_TRY(cudaSetDevice(ix->device));
-    // classify: append vs overwrite (InMemoryVectorStore insert semantics)
+    // classify: append vs overwrite (InMemoryVectorStore insert semantics).  New id -> row entries are STAGED and only
+    // committed to id2row once every copy has succeeded: a failed add (row limit, out of memory, copy error) must not leave
+    // ids that point at rows which were never stored.
     std::vector<uint64_t> target(n);
+    std::unordered_map<IdKey, uint64_t, IdHash> staged;
     uint64_t next = ix->n;
     for (uint64_t i = 0; i < n; ++i) {
         if (ids) {
             IdKey key = id_key(ids[i]);
             auto it = ix->id2row.find(key);
             if (it != ix->id2row.end()) { target[i] = it->second; continue; }
-            ix->id2row.emplace(key, next);
+            auto st = staged.find(key);
+            if (st != staged.end()) { target[i] = st->second; continue; }      // same new id twice in one call: last row wins
+            staged.emplace(key, next);
         }
         target[i] = next++;
     }
@@ -431,7 +471,10 @@ static int add_impl(cgvec_index* ix, const uint8_t (*ids)[16], const void* rows,
         i = j;
     }
     CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    for (auto& kv : staged) ix->id2row.emplace(kv.first, kv.second);
     ix->n = next;
+    ix->agreed_valid = false;
+    ix->n_codes = 0;                                            // int8 codes are stale after any write: cgvec_quantize_i8 again
     return CGVEC_OK;
 }
 
@@ -459,6 +502,7 @@ CGVEC_EXPORT int cgvec_normalize_rows(cgvec_index* ix) {
     int rc = launch_norms(ix, 0, ix->n, ix->main_stream);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
+    ix->n_codes = 0;
     return CGVEC_OK;
 }
 
@@ -490,6 +534,8 @@ CGVEC_EXPORT int cgvec_fill_synthetic(cgvec_index* ix, uint64_t n, uint64_t seed
     }
     CUDA_TRY(cudaStreamSynchronize(ix->main_stream));
     ix->n = next;
+    ix->agreed_valid = false;
+    ix->n_codes = 0;
     return CGVEC_OK;
 }
 
@@ -535,13 +581,16 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         return CGVEC_OK;
     }
     if (k > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u exceeds the fused top-k limit of %u", k, kMaxK);
-    if (ix->world > 1 && ix->n == 0) return fail(CGVEC_ERR_UNSUPPORTED, "a rank of a sharded index holds no rows");
+    if (ix->world > 1) {
+        if (!ix->agreed_valid) { int arc = agree_shard_sizes(ix); if (arc) return arc; }
+        if (ix->agreed_min_n == 0) return fail(CGVEC_ERR_UNSUPPORTED, "a rank of a sharded index holds no rows (every rank fails this call alike)");
+    }
 
     SearchCtx* c = nullptr;
     int rc = ctx_acquire(ix, &c);
     if (rc) return rc;
     cudaStream_t st = o.stream ? (cudaStream_t)o.stream : c->stream;
-    if (o.stream) cudaStreamWaitEvent(st, c->done, 0);         // scratch reuse across caller streams
+    cudaStreamWaitEvent(st, c->done, 0);                       // scratch reuse: the last user of this ctx may have been an asynchronous (device_io) call on another stream
     const uint32_t qstride = (ix->dim + 3) & ~3u;
     ix->searches++;
 
@@ -620,6 +669,8 @@ CGVEC_EXPORT int cgvec_search(const cgvec_index* ix, const float* queries, uint3
     o.path = CGVEC_PATH_AUTO;
     return cgvec_search_ex(ix, queries, nq, k, &o, out_rows, out_ids, out_scores, out_counts);
 }
+
+#include "stream_search.inl"
 
 template <typename T>
 static void launch_rescore_t(Index* ix, const float* d_q, const uint64_t* d_local_rows, uint32_t n, int metric, int formula,
@@ -744,9 +795,22 @@ CGVEC_EXPORT int cgvec_get_rows(const cgvec_index* cix, uint64_t first, uint64_t
         CUDA_TRY(cudaMemcpy2D(out, (size_t)ix->dim * 4, src, pitch, (size_t)ix->dim * 4, n, cudaMemcpyDeviceToHost));
         return CGVEC_OK;
     }
-    std::vector<uint16_t> tmp((size_t)n * ix->dim);
-    CUDA_TRY(cudaMemcpy2D(tmp.data(), (size_t)ix->dim * 2, src, pitch, (size_t)ix->dim * 2, n, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < tmp.size(); ++i) out[i] = __half2float(__ushort_as_half(tmp[i]));   // exact widening of stored bits
+    // f16 storage: widen on the device (exact), then copy f32 rows out in chunks
+    const uint64_t chunk = 1u << 16;
+    float* d_tmp = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_tmp), (size_t)(n < chunk ? n : chunk) * ix->dim * sizeof(float)));
+    cudaError_t e = cudaSuccess;
+    for (uint64_t r = 0; r < n && e == cudaSuccess; r += chunk) {
+        const uint64_t m = n - r < chunk ? n - r : chunk;
+        const uint64_t total = m * ix->dim;
+        widen_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ix->main_stream>>>(reinterpret_cast<const __half*>(src + r * pitch), ix->dim, ix->ld, m, d_tmp);
+        ix->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + r * ix->dim, d_tmp, total * sizeof(float), cudaMemcpyDeviceToHost, ix->main_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->main_stream);
+    }
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail(CGVEC_ERR_CUDA, "row read-back failed: %s", cudaGetErrorString(e));
     return CGVEC_OK;
 }
 
@@ -1110,6 +1174,9 @@ CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
     out->scans_timed = ix->scan_timed;
     out->tc_batches = ix->tc_batches.load();
     out->tc_fallbacks = ix->tc_fallbacks.load();
+    out->exchange_mode = ix->last_exchange.load();
+    out->tc_main_ms_total = ix->tc_main_ms_total;
+    out->tc_main_timed = ix->tc_main_timed;
     return CGVEC_OK;
 }
 
@@ -1123,7 +1190,7 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "l2_hint") ix->opt_l2_hint = (int)value;
     else if (k == "grid") ix->opt_grid = (int)value;
     else if (k == "timing") { ix->opt_timing = (int)value; if (!value) drain_timings(ix); }
-    else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; }
+    else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; ix->tc_main_ms_total = 0; ix->tc_main_timed = 0; }
     else if (k == "max_batch") ix->opt_max_nq = (int)value;
     else if (k == "pdl") ix->opt_pdl = (int)value;
     else if (k == "trace") {

@@ -168,6 +168,7 @@ int exchange_and_decode(Index* ix, SearchCtx* c, uint64_t* local_keys, uint32_t 
         std::lock_guard<std::mutex> lk(ix->comm_mu);
         NCCL_TRY(nccl_api().AllGather(local_keys, c->d_gather, per_rank, kNcclUint64, ix->comm, st));
     }
+    ix->last_exchange = 2;
     return merge_lists(ix, c, c->d_gather, nq, ix->world, k, ascending, nullptr, d_rows, d_scores, d_counts, st, (size_t)k, per_rank);
 }
 
@@ -233,7 +234,7 @@ int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t
     if (ix->opt_timing) {
         CUDA_TRY(cudaEventRecord(e1, st));
         std::lock_guard<std::mutex> lk(ix->ev_mu);
-        ix->timed.emplace_back(e0, e1);
+        ix->timed.push_back({e0, e1, 0});
     }
     ix->last_geom = g;
     if (partials_out) { *partials_out = partials; *lists_out = g.grid; return CGVEC_OK; }   // caller fuses merge + exchange
@@ -272,6 +273,7 @@ int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t 
                 CUDA_TRY(cudaLaunchKernelEx(&cfg, xchg_merge_kernel, xp));
             }
             ix->launches++;
+            ix->last_exchange = 1;
             return CGVEC_OK;
         }
         uint64_t* local_keys = nullptr;

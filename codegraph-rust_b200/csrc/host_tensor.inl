@@ -184,7 +184,6 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
         return CGVEC_OK;
     };
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
     if (ix->opt_tc_flow == 0) {
         // Bootstrap range (every row survives: thresholds are -inf) -> select -> ONE launch over the rest of the shard whose
         // selector warps keep tightening the thresholds in place -> select.  Unwritten list slots must read as 0.
@@ -199,7 +198,13 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
         rc = launch_range(0, S0, 0, 1); if (rc) return rc;
         rc = launch_select(S0 >= n ? 2u : 0u, (uint32_t)S0); if (rc) return rc;
         if (S0 < n) {
+            if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
             rc = launch_range(S0, n, 1); if (rc) return rc;
+            if (ix->opt_timing) {                                         // the dominant kernel: main range of the tensor scan
+                CUDA_TRY(cudaEventRecord(e1, st));
+                std::lock_guard<std::mutex> lk(ix->ev_mu);
+                ix->timed.push_back({e0, e1, 1});
+            }
             rc = launch_select(1); if (rc) return rc;
         }
     } else {
@@ -219,11 +224,6 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
             rc = launch_select(2); if (rc) return rc;
             T += S;
         }
-    }
-    if (ix->opt_timing) {
-        CUDA_TRY(cudaEventRecord(e1, st));
-        std::lock_guard<std::mutex> lk(ix->ev_mu);
-        ix->timed.emplace_back(e0, e1);
     }
     // exact re-score of the survivors, sort, proof
     {
@@ -288,7 +288,7 @@ int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uin
         tensor = true;
     } else if (path == CGVEC_PATH_AUTO) {
         const uint32_t min_nq = ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq;
-        tensor = tensor_path_applicable(ix, metric, nq) && nq >= min_nq && ix->n >= 4 * kTcCap && k <= kTcCap / 16;
+        tensor = tensor_path_applicable(ix, metric, nq) && nq >= min_nq && (ix->world > 1 ? ix->agreed_min_n : ix->n) >= 4 * kTcCap && k <= kTcCap / 16;   // rank-invariant
     }
     uint32_t n_max = tensor ? tc_batch_limit(ix, nq) : 0;
     if (tensor && n_max == 0) {
@@ -317,13 +317,14 @@ int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uin
 void drain_timings(Index* ix) {
     std::lock_guard<std::mutex> lk(ix->ev_mu);
     for (auto& pr : ix->timed) {
-        if (cudaEventSynchronize(pr.second) == cudaSuccess) {
+        if (cudaEventSynchronize(pr.e1) == cudaSuccess) {
             float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
-                ix->scan_ms_total += ms; ix->scan_timed++; ix->last_scan_ms = ms;
+            if (cudaEventElapsedTime(&ms, pr.e0, pr.e1) == cudaSuccess) {
+                if (pr.kind == 0) { ix->scan_ms_total += ms; ix->scan_timed++; ix->last_scan_ms = ms; }
+                else { ix->tc_main_ms_total += ms; ix->tc_main_timed++; }
             }
         }
-        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1);
     }
     ix->timed.clear();
 }

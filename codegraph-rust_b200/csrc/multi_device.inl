@@ -135,13 +135,16 @@ int multi_add(Index* mx, const uint8_t (*ids)[16], const void* rows, uint64_t n,
     if (src_esize != mx->esize)
         return fail(CGVEC_ERR_BAD_ARG, "index stores %s rows; use %s", mx->esize == 4 ? "f32" : "f16", mx->esize == 4 ? "cgvec_add" : "cgvec_add_f16");
     std::vector<uint64_t> target(n);
+    std::unordered_map<IdKey, uint64_t, IdHash> staged;            // committed only after every copy succeeded (see add_impl)
     uint64_t next = mx->n;
     for (uint64_t i = 0; i < n; ++i) {
         if (ids) {
             IdKey key = id_key(ids[i]);
             auto it = mx->id2row.find(key);
             if (it != mx->id2row.end()) { target[i] = it->second; continue; }
-            mx->id2row.emplace(key, next);
+            auto st = staged.find(key);
+            if (st != staged.end()) { target[i] = st->second; continue; }
+            staged.emplace(key, next);
         }
         target[i] = next++;
     }
@@ -161,6 +164,7 @@ int multi_add(Index* mx, const uint8_t (*ids)[16], const void* rows, uint64_t n,
     }
     int rc = multi_sync(mx);
     if (rc) return rc;
+    for (auto& kv : staged) mx->id2row.emplace(kv.first, kv.second);
     mx->n = next;
     return CGVEC_OK;
 }

@@ -321,8 +321,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
         }
         while (next_boundary < my_tiles) { sync_and_maybe_compact(false); next_boundary += epoch; }
         sync_and_maybe_compact(true);
-        // sorted best-k keys of this CTA (0-padded)
-        if (p.early_trigger) asm volatile("griddepcontrol.wait;" ::: "memory");
+        // sorted best-k keys of this CTA (0-padded).  The wait orders this WRITE after the kernel ahead of us in the stream
+        // whenever we were launched with the programmatic attribute — also when we did not release our own dependents
+        // early (a grid smaller than the SM count): otherwise a small shard's scan could overwrite the double-buffered
+        // lists / let the next exchange run while the previous one still spins on a slow peer.  It is a no-op for a
+        // plain launch.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
             const uint32_t cnt = s_count[j];

@@ -133,6 +133,19 @@ int cgvec_search_ex(const cgvec_index* idx, const float* queries, uint32_t nq, u
                     const cgvec_search_opts* opts,
                     uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts);
 
+/* ---- streaming batches (BASELINE config 5): many query embeddings against one store, the shape of
+ * SemanticSearch::multi_vector_search (codegraph-vector/src/search.rs:347-361), fed batch after batch from HOST memory.
+ * cgvec_stream_submit stages batch i+1 (pinned copy + asynchronous upload on a copy stream) and then runs the search of
+ * batch i, so uploads travel behind the scan; results therefore lag one submit (*out_nq = 0 on the first call) and
+ * cgvec_stream_flush drains the last batch.  Outputs are host buffers of max_batch*k (rows, scores) and max_batch
+ * (counts) entries.  On a sharded index every rank submits the same batches (the exchange inside is collective). */
+typedef struct cgvec_stream cgvec_stream;
+int cgvec_stream_open(cgvec_index* idx, uint32_t max_batch, uint32_t k, cgvec_metric metric, cgvec_path path, cgvec_stream** out);
+int cgvec_stream_submit(cgvec_stream* s, const float* queries /* nq x dim, host */, uint32_t nq, uint64_t* out_rows,
+                        float* out_scores, uint32_t* out_counts, uint32_t* out_nq);
+int cgvec_stream_flush(cgvec_stream* s, uint64_t* out_rows, float* out_scores, uint32_t* out_counts, uint32_t* out_nq);
+int cgvec_stream_close(cgvec_stream* s);
+
 /* VectorStore::get_embedding: copies the row (widened to f32) into out_row[dim]; CGVEC_ERR_NOT_FOUND -> None. */
 int cgvec_get(const cgvec_index* idx, const uint8_t id[16], float* out_row);
 int cgvec_get_row(const cgvec_index* idx, uint64_t local_row, float* out_row);
@@ -194,6 +207,10 @@ typedef struct {
     uint64_t scans_timed;
     uint64_t tc_batches;         /* query batches served by the tensor-core path                         */
     uint64_t tc_fallbacks;       /* queries it could not prove exact and re-ran on the exact-order kernel */
+    uint32_t exchange_mode;      /* last top-k exchange of a sharded index: 0 none, 1 fused NVLink peer-memory kernel, 2 NCCL all-gather */
+    uint32_t reserved0;
+    double tc_main_ms_total;     /* sum / count of device times of the tensor scan's main-range kernel ("timing" on) */
+    uint64_t tc_main_timed;
 } cgvec_stats;
 int cgvec_get_stats(const cgvec_index* idx, cgvec_stats* out);
 int cgvec_set_option(cgvec_index* idx, const char* key, int64_t value);   /* tuning knobs, see DESIGN.md */

@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -491,10 +492,38 @@ CG_API void cg_vecs_destroy(void* h) {
     for (uint64_t i = 0; i < v->n; ++i) free(v->rows[i]);
     free(v->rows); free(v);
 }
-CG_API int cg_max_threads(void) {
+/* Threads worth starting: online CPUs, clipped by the affinity mask AND by the cgroup CPU quota (cpu.max of cgroup v2,
+ * cpu.cfs_quota_us / cpu.cfs_period_us of v1): a container limited to 32 CPUs' worth of time on a 128-thread host
+ * gains nothing from 128 threads, and a baseline that reports "128 cores" there misstates what it ran on. */
+static long cg_cgroup_cpu_limit(void) {
+    FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char a[64]; long period = 0; long lim = 0;
+        if (fscanf(f, "%63s %ld", a, &period) == 2 && strcmp(a, "max") != 0 && period > 0) {
+            long quota = atol(a);
+            if (quota > 0) lim = (quota + period - 1) / period;
+        }
+        fclose(f);
+        if (lim > 0) return lim;
+    }
+    long quota = 0, period = 0;
+    f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+    if (f) { if (fscanf(f, "%ld", &quota) != 1) quota = 0; fclose(f); }
+    f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+    if (f) { if (fscanf(f, "%ld", &period) != 1) period = 0; fclose(f); }
+    if (quota > 0 && period > 0) return (quota + period - 1) / period;
+    return 0;
+}
+CG_API int cg_affinity_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) { int c = CPU_COUNT(&set); if (c > 0 && c < n) n = c; }
+    return n > 0 ? (int)n : 1;
+}
+CG_API int cg_max_threads(void) {
+    long n = cg_affinity_threads();
+    long q = cg_cgroup_cpu_limit();
+    if (q > 0 && q < n) n = q;
     return n > 0 ? (int)n : 1;
 }
 /* minimal fork-join over T workers (stands in for rayon's pool) */
@@ -584,6 +613,52 @@ CG_API uint64_t cg_fair_top_k_search_mt(const float* q, const float* rows, uint6
     for (uint64_t i = 0; i < r; ++i) { out_idx[i] = all[i].idx; out_score[i] = all[i].score; }
     free(all); free(cnt); free(part);
     return r;
+}
+
+/* The same function for nq queries in ONE pass over the rows (each row is scored against every query while it is in
+ * cache): the bench's parity legs check several queries of a batch against multi-GB shards, and a pass per query is
+ * bound by host memory bandwidth.  Outputs are cg_parallel_top_k_search's, per query: out_idx / out_score [nq][k]
+ * (entries beyond out_cnt[q] are untouched). */
+typedef struct { const float* qs; uint64_t nq; const float* flat; cg_pair* p; uint64_t n, blk, m; size_t d; uint64_t* cnt; int T; } cg_mtq;
+static void cg_mt_fair_multi(int t, int T, void* a) {
+    cg_mtq* c = (cg_mtq*)a; (void)T;
+    uint64_t lo = (uint64_t)t * c->blk, hi = lo + c->blk > c->n ? c->n : lo + c->blk, m = c->m;
+    for (uint64_t qi = 0; qi < c->nq; ++qi) c->cnt[qi * c->T + t] = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        const float* row = c->flat + i * c->d;
+        for (uint64_t qi = 0; qi < c->nq; ++qi) {
+            cg_pair* b = c->p + (qi * c->T + (uint64_t)t) * m; uint64_t cn = c->cnt[qi * c->T + t];
+            cg_pair x; x.idx = i; x.score = cg_adaptive_cosine_similarity(c->qs + qi * c->d, row, c->d);
+            if (cn == m && cg_cmp_desc(&x, &b[cn - 1]) >= 0) continue;
+            uint64_t j = cn < m ? cn++ : cn - 1;
+            while (j > 0 && cg_cmp_desc(&x, &b[j - 1]) < 0) { b[j] = b[j - 1]; --j; }
+            b[j] = x;
+            c->cnt[qi * c->T + t] = cn;
+        }
+    }
+}
+CG_API void cg_fair_top_k_search_multi(const float* qs, uint64_t nq, const float* rows, uint64_t n, size_t d, uint64_t k,
+                                       int threads, uint64_t* out_idx, float* out_score, uint64_t* out_cnt) {
+    for (uint64_t qi = 0; qi < nq; ++qi) out_cnt[qi] = 0;
+    if (n == 0 || k == 0 || nq == 0) return;
+    int T = threads > 0 ? threads : cg_max_threads();
+    if ((uint64_t)T > n) T = (int)n;
+    uint64_t m = k < n ? k : n;
+    cg_pair* part = (cg_pair*)malloc(sizeof(cg_pair) * m * T * nq);
+    uint64_t* cnt = (uint64_t*)calloc((size_t)T * nq, sizeof(uint64_t));
+    uint64_t blk = (n + T - 1) / T;
+    cg_mtq ctx; memset(&ctx, 0, sizeof(ctx)); ctx.qs = qs; ctx.nq = nq; ctx.flat = rows; ctx.p = part; ctx.n = n; ctx.blk = blk; ctx.d = d; ctx.m = m; ctx.cnt = cnt; ctx.T = T;
+    cg_fork_join(T, cg_mt_fair_multi, &ctx);
+    cg_pair* all = (cg_pair*)malloc(sizeof(cg_pair) * m * T);
+    for (uint64_t qi = 0; qi < nq; ++qi) {
+        uint64_t o = 0;
+        for (int t = 0; t < T; ++t) { memcpy(all + o, part + (qi * T + (uint64_t)t) * m, sizeof(cg_pair) * cnt[qi * T + t]); o += cnt[qi * T + t]; }
+        qsort(all, o, sizeof(cg_pair), cg_cmp_desc);
+        uint64_t r = m < o ? m : o;
+        for (uint64_t i = 0; i < r; ++i) { out_idx[qi * k + i] = all[i].idx; out_score[qi * k + i] = all[i].score; }
+        out_cnt[qi] = r;
+    }
+    free(all); free(cnt); free(part);
 }
 
 /* ------------------------------------------------------------------------------------------

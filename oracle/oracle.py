@@ -68,6 +68,9 @@ def lib():
         L.cg_vecs_create.restype = C.c_void_p; L.cg_vecs_create.argtypes = [fp, C.c_uint64, C.c_size_t]
         L.cg_vecs_destroy.restype = None; L.cg_vecs_destroy.argtypes = [C.c_void_p]
         L.cg_max_threads.restype = C.c_int
+        L.cg_affinity_threads.restype = C.c_int
+        L.cg_fair_top_k_search_multi.restype = None
+        L.cg_fair_top_k_search_multi.argtypes = [fp, C.c_uint64, fp, C.c_uint64, C.c_size_t, C.c_uint64, C.c_int, u64p, fp, u64p]
         L.cg_have_avx2.restype = C.c_int
         L.cg_parallel_top_k_search_mt.restype = C.c_uint64
         L.cg_parallel_top_k_search_mt.argtypes = [fp, C.c_void_p, C.c_uint64, C.c_int, u64p, fp]
@@ -261,8 +264,33 @@ def fair_top_k_mt(query, rows, k, threads=0):
     return idx[:got].copy(), sc[:got].copy()
 
 
+def fair_top_k_multi(queries, rows, k, threads=0):
+    """cg_parallel_top_k_search's outputs for several queries in one pass over `rows` -> list of (indices, scores)."""
+    qs, r = _f32(queries), _f32(rows)
+    nq = qs.shape[0]
+    idx = np.zeros((nq, max(k, 1)), np.uint64); sc = np.zeros((nq, max(k, 1)), np.float32); cnt = np.zeros(nq, np.uint64)
+    lib().cg_fair_top_k_search_multi(_fp(qs), nq, _fp(r), r.shape[0], r.shape[1], k, threads,
+                                     idx.ctypes.data_as(C.POINTER(C.c_uint64)), _fp(sc), cnt.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return [(idx[i, :int(cnt[i])].copy(), sc[i, :int(cnt[i])].copy()) for i in range(nq)]
+
+
+def merge_top_k(parts, k):
+    """Merges per-chunk (global indices, scores) lists under the result contract (best first, ties -> lower row, NaN last)."""
+    idx = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.uint64)
+    sc = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.float32)
+    nan = np.isnan(sc)
+    key = np.where(nan, -np.inf, sc.astype(np.float64))
+    order = np.lexsort((idx, -key, nan))            # primary: non-NaN first, then score descending, then row ascending
+    order = order[:k]
+    return idx[order], sc[order]
+
+
 def max_threads():
     return int(lib().cg_max_threads())
+
+
+def affinity_threads():
+    return int(lib().cg_affinity_threads())
 
 
 def synth_rows(seed, first_row, n, d, unit_norm=True, f16=False, threads=0):

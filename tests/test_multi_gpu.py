@@ -142,3 +142,93 @@ def test_sharded_tensor_path_equals_oracle(oracle, dtype_name, k):
                 wi, ws = oracle.parallel_top_k_search(qs[qi], ref, k)
                 assert gr[qi] == wi.tolist()
                 assert got_s[qi].tobytes() == ws.tobytes()
+
+
+def _worker_general(rank, world, uid_q, rows, qs, k, out, bounds, dtype_name, path_name, reps, skew_rank):
+    """Like _worker, with explicit shard boundaries, repeated calls and a host-side delay on one rank between calls (rank
+    skew: the other ranks' exchange kernels spin on this rank's flags while their next scans are already queued)."""
+    sys.path.insert(0, ROOT)
+    import time
+    import __graft_entry__ as ge
+    cg = ge.load_package()
+    import torch
+    torch.cuda.set_device(rank)
+    if rank == 0:
+        uid = cg.nccl_unique_id()
+        for _ in range(world - 1):
+            uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    b, e = bounds[rank], bounds[rank + 1]
+    dt = cg.F32 if dtype_name == "f32" else cg.F16
+    ix = cg.Index(rows.shape[1], dt, device=rank, rank=rank, world=world, nccl_unique_id=uid, row_offset=b)
+    ix.add(rows[b:e])
+    path = {"auto": cg.PATH_AUTO, "tensor": cg.PATH_TENSOR, "exact": cg.PATH_EXACT}[path_name]
+    res = []
+    rng = np.random.default_rng(rank)
+    for it in range(reps):
+        if rank == skew_rank:
+            time.sleep(float(rng.uniform(0.0, 0.02)))
+        r, s, c = ix.search(qs[it % len(qs)], k, cg.COSINE, path=path)
+        res.append((r.tolist(), s.tobytes(), c.tolist()))
+    st = ix.stats()
+    out[rank] = (res, int(st.tc_batches), int(st.tc_fallbacks), int(st.exchange_mode))
+    ix.close()
+
+
+def _run_general(oracle, rows, qsets, k, bounds, dtype_name="f32", path_name="auto", reps=1, skew_rank=-1):
+    import torch.multiprocessing as mp
+    world = len(bounds) - 1
+    ref = rows if dtype_name == "f32" else rows.astype(np.float16).astype(np.float32)
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict(); uid_q = ctx.Queue()
+        procs = [ctx.Process(target=_worker_general, args=(r, world, uid_q, rows, qsets, k, out, bounds, dtype_name, path_name, reps, skew_rank))
+                 for r in range(world)]
+        [p.start() for p in procs]
+        for p in procs:
+            p.join(600)
+            assert p.exitcode == 0, "a rank failed or hung"
+        want = {}
+        for r in range(world):
+            res = out[r][0]
+            for it in range(reps):
+                qs = qsets[it % len(qsets)]
+                gr, gs, gc = res[it]
+                got_s = np.frombuffer(gs, np.float32).reshape(len(qs), k)
+                for qi in range(len(qs)):
+                    key = (it % len(qsets), qi)
+                    if key not in want:
+                        want[key] = oracle.parallel_top_k_search(qs[qi], ref, k)
+                    wi, ws = want[key]
+                    assert gr[qi][:len(wi)] == wi.tolist(), (r, it, qi)
+                    assert got_s[qi][:len(ws)].tobytes() == ws.tobytes(), (r, it, qi)
+        return {r: out[r][1:] for r in range(world)}
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_tiny_shards_many_queries_under_rank_skew(oracle):
+    """Shards far smaller than one tile per SM (the scan grid does not fill the GPU, so it never releases its dependents
+    early), 14 queries per call (four chained scan -> exchange steps) and one rank that dawdles between calls: the
+    double-buffered per-CTA lists and the two-parity exchange slots must never be overwritten early (ADVICE r01 #1)."""
+    world = min(_ngpus(), 4)
+    rng = np.random.default_rng(77)
+    n, d, k = 1_500 * world, 128, 10
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    qsets = [rng.standard_normal((14, d)).astype(np.float32) for _ in range(3)]
+    bounds = [n * r // world for r in range(world + 1)]
+    st = _run_general(oracle, rows, qsets, k, bounds, "f32", "exact", reps=40, skew_rank=world - 1)
+    assert all(v[2] == 1 for v in st.values()), "the fused peer-memory exchange should have carried these calls"
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_uneven_shards_take_the_same_path_on_every_rank(oracle):
+    """Rank 0 holds enough rows for the tensor path under AUTO, the last rank does not: the decision must be taken on a
+    rank-invariant quantity or the ranks issue different collectives and hang (ADVICE r01 #2)."""
+    world = 2
+    rng = np.random.default_rng(78)
+    n, d, k = 70_000, 128, 10
+    rows = (rng.standard_normal((n, d)) / 11).astype(np.float32)
+    qsets = [rng.standard_normal((64, d)).astype(np.float32)]
+    st = _run_general(oracle, rows, qsets, k, [0, 40_000, 70_000], "f16", "auto", reps=2)
+    assert len({v[0] > 0 for v in st.values()}) == 1, "ranks disagreed on the kernel family"

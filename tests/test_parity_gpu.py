@@ -497,3 +497,33 @@ def test_parallel_vector_ops_mirror(cg, oracle):
     assert sims.tobytes() == oracle.scores(q, emb).tobytes()
     norm = cg.ParallelVectorOps.parallel_normalize_vectors(emb)
     assert norm.tobytes() == np.stack([oracle.normalize_avx2(r) for r in emb]).tobytes()
+
+
+def test_query_stream_double_buffered_batches(cg, oracle):
+    """cgvec_stream_*: batches submitted one after the other (upload of batch i+1 behind the scan of batch i) return
+    exactly what one-shot searches return, in order, including a short last batch; flush drains the pipeline."""
+    rng = np.random.default_rng(91)
+    n, d, k = 50_000, 256, 10
+    rows = (rng.standard_normal((n, d)) / 16).astype(np.float32)
+    ix = cg.Index(d, cg.F16)
+    try:
+        ix.add(rows)
+        ref = rows.astype(np.float16).astype(np.float32)
+        batches = [rng.standard_normal((m, d)).astype(np.float32) for m in (64, 64, 17, 64)]
+        stream = ix.stream(64, k, cg.COSINE, cg.PATH_AUTO)
+        got = []
+        assert stream.submit(batches[0]) is None                 # nothing to return yet
+        for b in batches[1:]:
+            got.append(stream.submit(b))
+        got.append(stream.flush())
+        assert stream.flush() is None
+        stream.close()
+        for b, (r, s, c) in zip(batches, got):
+            assert r.shape == (len(b), k)
+            for qi in range(0, len(b), 5):
+                wi, ws = oracle.parallel_top_k_search(b[qi], ref, k)
+                assert r[qi].tolist() == wi.tolist() and s[qi].tobytes() == ws.tobytes() and int(c[qi]) == k
+        with pytest.raises(cg.CgvecError):
+            ix.stream(64, k).submit(np.zeros((65, d), np.float32))
+    finally:
+        ix.close()
