@@ -561,6 +561,58 @@ class SemanticSearch:
         return [SearchResult(ids[j], float(s)) for j, s in zip(order, norm)]
 
 
+@dataclass
+class ChunkRecord:
+    """The fields of a `chunks` row the candidate stage reads (schema/codegraph.surql:331-345): its id, its parent node
+    (None for orphan chunks) and its embedding."""
+    id: _uuid.UUID
+    parent_node: Optional[_uuid.UUID]
+    embedding: Sequence[float]
+
+
+@dataclass
+class ChunkCandidate:
+    node_id: _uuid.UUID          # parent node of the chunk hit (<string> parent_node AS node_id, codegraph.surql:403)
+    vector_score: float          # 1f - distance (codegraph.surql:412)
+    chunk_id: _uuid.UUID
+
+
+class ChunkCandidateStage:
+    """Step 1-2 of fn::semantic_search_nodes_via_chunks (schema/codegraph.surql:318-417), the vector stage behind
+    execute_semantic_code_search (codegraph-mcp-tools/src/graph_tool_executor.rs:578-591): the 100 nearest chunk
+    embeddings (`<|100,200|>`), minus chunks without a parent node, cut to 3 x safe_limit rows (safe_limit = limit when
+    1 <= limit <= 100, else 10), each mapped to (parent node, 1 - cosine distance).  The KNN itself is the EXACT
+    brute-force scan of this library (B200Backend.vector_knn) in place of SurrealDB's approximate HNSW; BM25, the 0.9/0.1
+    blend and the graph enrichment stay in SurrealDB."""
+
+    KNN = 100                                   # the literal of `<|100,200|>`
+
+    def __init__(self, dimension: int, dtype: int = F32, device: int = 0, devices: Optional[Sequence[int]] = None):
+        self.store = B200VectorStore(dimension, dtype, device, devices)
+        self.backend = B200Backend(self.store)
+        self.parent: dict = {}                  # chunk id -> parent node id | None
+
+    def upsert_chunks(self, chunks: Sequence[ChunkRecord]) -> None:
+        self.backend.upsert_nodes([CodeNode(c.id, c.embedding) for c in chunks])
+        for c in chunks:
+            self.parent[c.id] = c.parent_node
+
+    def candidates(self, query_embedding, limit: int) -> List[ChunkCandidate]:
+        safe_limit = limit if 0 < limit <= 100 else 10                              # codegraph.surql:325
+        chunk_limit = safe_limit * 3                                                # :326
+        hits = self.backend.vector_knn(f"embedding_{self.store.index.dim}", query_embedding, self.KNN)   # :334-339, ascending distance
+        out: List[ChunkCandidate] = []
+        for rid, distance in hits:
+            cid = _uuid.UUID(rid.split(":", 1)[1])
+            parent = self.parent.get(cid)
+            if parent is None:                                                      # parent_node != NONE
+                continue
+            out.append(ChunkCandidate(parent, float(np.float32(1.0) - np.float32(distance)), cid))
+            if len(out) == chunk_limit:                                             # LIMIT $chunk_limit
+                break
+        return out
+
+
 def resolve_symbol(index: "Index", target_embedding, candidate_rows, threshold: float = 0.75):
     """AI symbol resolver arg-max (codegraph-mcp/src/indexer.rs:2827-2843, cosine :2965-2979): among the candidate rows
     that survived the caller's trigram prefilter, the FIRST row with the highest cosine (search.rs:519-533 arithmetic,
@@ -578,9 +630,11 @@ def resolve_symbol(index: "Index", target_embedding, candidate_rows, threshold: 
 
 def resolve_symbols(index: "Index", target_embeddings, threshold: float = 0.75):
     """The resolver's arg-max for U unresolved references at once, over ALL symbol rows of `index` instead of a trigram
-    prefilter (codegraph-mcp/src/indexer.rs:2673-2878 runs the U loop with rayon, :1914,1983): one k=1 scan per target
-    under the sequential cosine (search.rs:519-533), ties to the lower row = the reference's "first best wins" in row
-    order; entries at or below `threshold` become None.  -> [ (row, similarity) | None ] * U"""
+    prefilter (codegraph-mcp/src/indexer.rs:2673-2878 runs the U loop with rayon, :1914,1983).  With U >= 8 (16 for f32
+    storage) and >= 32768 symbols this is ONE dense U x S pass on the tensor cores per 256 references (k = 1, survivors
+    re-scored in the sequential cosine of search.rs:519-533 / indexer.rs:2965-2979, exactness proven on the device);
+    smaller problems take one exact scan per reference.  Ties go to the lower row = the reference's "first best wins"
+    in row order; entries at or below `threshold` become None.  -> [ (row, similarity) | None ] * U"""
     t = np.ascontiguousarray(target_embeddings, np.float32)
     if t.ndim == 1:
         t = t[None, :]

@@ -151,7 +151,9 @@ __global__ void make_keys_kernel(const float* __restrict__ scores, const uint64_
 }
 
 // ---- K5 -------------------------------------------------------------------------------------------
-// in  : [nq][n_lists][list_len] keys (each list sorted or not — the CTA sorts), 0 = empty
+// in  : keys of list l of query q at in + q * q_stride + l * l_stride (list_len keys each, sorted or not — the CTA sorts), 0 = empty;
+//       the contiguous [nq][n_lists][list_len] layout is q_stride = n_lists * list_len, l_stride = list_len, the gathered
+//       [rank][nq][k] layout of the exchange is q_stride = k, l_stride = nq * k (no re-packing copies)
 // out : [nq][n_out][k]   where CTA (x, y) merges lists [x*lists_per_cta, ...) of query y and keeps the best k.
 // When out_rows/out_scores/out_counts are given (final level, n_out == 1) the winners are decoded too.
 constexpr int kMergeThreads = 256;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
                                                                     uint64_t* __restrict__ out_rows,
                                                                     float* __restrict__ out_scores,
                                                                     uint32_t* __restrict__ out_counts, int sorted_in,
-                                                                    uint64_t* trace) {
+                                                                    uint64_t* trace, uint64_t q_stride, uint64_t l_stride) {
     extern __shared__ __align__(16) uint64_t s_merge_keys[];
     uint64_t* s_keys = s_merge_keys;
     if (threadIdx.x == 0) trace_begin(trace);
@@ -174,14 +176,15 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
     const uint32_t q = blockIdx.y, n_out = gridDim.x;
     const uint32_t first = blockIdx.x * lists_per_cta;
     const uint32_t lists = min(lists_per_cta, n_lists - first);
-    const uint64_t* src = in + ((size_t)q * n_lists + first) * list_len;
+    const uint64_t* src = in + (size_t)q * q_stride + (size_t)first * l_stride;
     const uint32_t total = lists * list_len;
+    const bool dense = l_stride == list_len;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t* best;                                       // the CTA's best-k keys, descending, 0-padded
     if (sorted_in && k <= kTournamentMaxK && lists <= 32 * (kMergeThreads / 32)) {
         // tournament: every warp reduces up to 32 sorted lists to one, then warp 0 reduces the <= 8 survivors
         uint64_t* lvl = s_keys + sort_n;                        // [8][k] after the staged lists
-        for (uint32_t i = threadIdx.x; i < total; i += kMergeThreads) s_keys[i] = src[i];
+        for (uint32_t i = threadIdx.x; i < total; i += kMergeThreads) s_keys[i] = dense ? src[i] : src[(size_t)(i / list_len) * l_stride + i % list_len];
         __syncthreads();
         const uint32_t nw = (lists + 31) / 32;
         if (warp < nw)
@@ -195,7 +198,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
             best = lvl;
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < sort_n; i += kMergeThreads) s_keys[i] = (i < total) ? src[i] : 0ull;
+        for (uint32_t i = threadIdx.x; i < sort_n; i += kMergeThreads)
+            s_keys[i] = (i < total) ? (dense ? src[i] : src[(size_t)(i / list_len) * l_stride + i % list_len]) : 0ull;
         __syncthreads();
         bitonic_sort_desc(s_keys, sort_n, threadIdx.x, kMergeThreads, 0);
         best = s_keys;

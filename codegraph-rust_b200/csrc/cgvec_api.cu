@@ -129,6 +129,8 @@ struct Index {
     int32_t* d_inorms = nullptr;
     uint64_t n_codes = 0;
     uint32_t ld8 = 0;
+    std::mutex i8_mu;
+    std::unordered_map<uint32_t, uint64_t> i8_fill_end;   // limit -> row of the limit-th non-zero-norm code row (valid while the codes are)
 
     std::vector<uint8_t> ids;     // 16 bytes per local row
     std::vector<uint8_t> has_id;  // 1 per local row
@@ -142,6 +144,8 @@ struct Index {
     bool p2p = false;
     uint32_t xseq = 0;
     int opt_p2p = 1;
+    uint32_t* h_xerr = nullptr;   // pinned, device-visible: the exchange kernel reports a rank whose list never arrived
+    int opt_xchg_timeout_ms = 5000;
 
     // rank-invariant view of a sharded index: smallest / largest shard, agreed with one all-gather after the rows change
     uint64_t agreed_min_n = 0, agreed_max_n = 0;
@@ -317,6 +321,9 @@ int agree_shard_sizes(Index* ix) {
     return CGVEC_OK;
 }
 
+int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st, uint64_t* h_rows, float* h_scores,
+                   uint32_t* h_count);
+
 #include "host_scan.inl"
 #include "host_tensor.inl"
 }  // namespace
@@ -358,6 +365,8 @@ static int create_common(uint32_t dim, cgvec_dtype storage, int device, int rank
         NcclUniqueId id;
         memcpy(&id, uid, sizeof(id));
         NCCL_TRY(nccl_api().CommInitRank(&ix->comm, world, id, rank));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ix->h_xerr), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        *ix->h_xerr = 0;
         setup_peer_exchange(ix.get());            // best effort: NCCL remains the transport if peer mapping fails
     }
     *out = ix.release();
@@ -404,6 +413,7 @@ CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
     for (int r = 0; r < ix->world && r < (int)kXchgMaxWorld; ++r)
         if (ix->xpeer[r] && r != ix->rank) cudaIpcCloseMemHandle(ix->xpeer[r]);
     cudaFree(ix->xbuf);
+    cudaFreeHost(ix->h_xerr);
     if (ix->comm) nccl_api().CommDestroy(ix->comm);
     cudaFree(ix->d_rows);
     cudaFree(ix->d_norms);
@@ -547,8 +557,6 @@ CGVEC_EXPORT uint32_t cgvec_dim(const cgvec_index* ix) { return ix ? ix->dim : 0
 
 // formula != SIMD: over-fetch with the exact SIMD-order scan, re-score the candidates in the requested
 // formula on the device, re-rank, and PROVE no outside row can enter the top-k (else widen and retry).
-static int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st,
-                          uint64_t* h_rows, float* h_scores, uint32_t* h_count);
 
 CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, uint32_t nq, uint32_t k,
                                  const cgvec_search_opts* opts, uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores,
@@ -582,6 +590,7 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
     }
     if (k > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u exceeds the fused top-k limit of %u", k, kMaxK);
     if (ix->world > 1) {
+        if (ix->h_xerr && *ix->h_xerr) return fail(CGVEC_ERR_NCCL, "an earlier peer exchange timed out waiting for rank %u; the sharded index is out of step and must be rebuilt", *ix->h_xerr - 1);
         if (!ix->agreed_valid) { int arc = agree_shard_sizes(ix); if (arc) return arc; }
         if (ix->agreed_min_n == 0) return fail(CGVEC_ERR_UNSUPPORTED, "a rank of a sharded index holds no rows (every rank fails this call alike)");
     }
@@ -633,9 +642,21 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
         if (rc) return finish(rc);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return finish(fail(CGVEC_ERR_CUDA, "search failed on the device: %s", cudaGetErrorString(e)));
+        if (ix->h_xerr && *ix->h_xerr) return finish(fail(CGVEC_ERR_NCCL, "peer exchange timed out after %d ms waiting for rank %u", ix->opt_xchg_timeout_ms, *ix->h_xerr - 1));
     } else {
         if (ix->world > 1 || ix->row_offset != 0) return finish(fail(CGVEC_ERR_UNSUPPORTED, "non-SIMD formulas are not available on sharded indexes yet"));
-        for (uint32_t q = 0; q < nq; ++q) {
+        // A batch under a sequential cosine (the indexer's symbol resolver: U references x S symbols, indexer.rs:2827-2843) is a
+        // dense contraction like any other: ONE tensor-core pass orders the rows, the survivors are re-scored in the formula's own
+        // order, and the proof's bound grows by |formula - simd|.  Small batches and the distance form keep the per-query path.
+        const bool batched = o.formula != CGVEC_FORMULA_BASELINE && o.path != CGVEC_PATH_EXACT && tensor_auto_ok(ix, o.metric, nq, k) &&
+                             tc_batch_limit(ix, nq) > 0;
+        if (batched) {
+            rc = run_queries(ix, c, c->d_q, qstride, nq, k, o.metric, CGVEC_PATH_TENSOR, st, c->h_rows, c->h_scores, c->h_counts, o.formula);
+            if (rc) return finish(rc);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return finish(fail(CGVEC_ERR_CUDA, "search failed on the device: %s", cudaGetErrorString(e)));
+        }
+        for (uint32_t q = 0; q < nq && !batched; ++q) {
             rc = search_formula(ix, c, c->d_q + (size_t)q * qstride, k, o.formula, st, c->h_rows + (size_t)q * k, c->h_scores + (size_t)q * k,
                                 c->h_counts + q);
             if (rc) return finish(rc);
@@ -681,8 +702,9 @@ static void launch_rescore_t(Index* ix, const float* d_q, const uint64_t* d_loca
     ix->launches++;
 }
 
-static int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st, uint64_t* h_rows,
-                          float* h_scores, uint32_t* h_count) {
+namespace {
+int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st, uint64_t* h_rows,
+                   float* h_scores, uint32_t* h_count) {
     const int ascending = (formula == CGVEC_FORMULA_BASELINE);
     const uint64_t n = ix->n;
     const uint32_t want = (uint32_t)(k < n ? k : n);
@@ -744,6 +766,8 @@ static int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k,
         kp *= 2;
     }
 }
+
+}  // namespace
 
 CGVEC_EXPORT int cgvec_row_of_id(const cgvec_index* ix, const uint8_t id[16], uint64_t* out_local_row) {
     if (!ix || !id) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
@@ -900,10 +924,12 @@ CGVEC_EXPORT int cgvec_quantize_i8(cgvec_index* ix) {
     CUDA_TRY(cudaSetDevice(ix->device));
     cudaFree(ix->d_codes); cudaFree(ix->d_inorms);
     ix->d_codes = nullptr; ix->d_inorms = nullptr; ix->n_codes = 0;
+    { std::lock_guard<std::mutex> lk(ix->i8_mu); ix->i8_fill_end.clear(); }
     ix->ld8 = (ix->dim + 15) & ~15u;
     if (ix->n == 0) return CGVEC_OK;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ix->d_codes), ix->n * (size_t)ix->ld8));
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ix->d_inorms), ix->n * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ix->d_inorms), (ix->n + 64) * sizeof(int32_t)));   // the scan's norm tiles read whole 32-row slots
+    CUDA_TRY(cudaMemsetAsync(ix->d_inorms, 0, (ix->n + 64) * sizeof(int32_t), ix->main_stream));
     const int threads = 256;
     const uint64_t blocks = (ix->n * 32 + threads - 1) / threads;
     if (ix->dtype == CGVEC_F32)
@@ -927,20 +953,106 @@ CGVEC_EXPORT int cgvec_get_codes_i8(const cgvec_index* cix, uint64_t first, uint
     return CGVEC_OK;
 }
 
+// One pass of scan_i8_kernel + merge: the best k keys (tie_mode 0: by score then lower row; tie_mode 1: the k lowest rows with
+// score >= vstar) read back to the host.
+static int i8_pass(Index* ix, SearchCtx* c, const int8_t* d_q8, const float* d_qn, const int32_t* d_qs, uint32_t k, uint32_t tie_mode, float vstar,
+                   cudaStream_t st, std::vector<uint64_t>* rows, std::vector<float>* scores, uint32_t* cnt_out) {
+    // The int8 codes go through the same TMA-staged, persistent scan kernel as the f32 / f16 matrix (scan_exact.cuh, METRIC_I8):
+    // rows of ld8 bytes are bulk-copied into the shared-memory ring as ld8/4 words, 8 threads per row run dp4a over them.
+    const uint32_t words = ix->ld8 / 4;
+    ScanGeom g;
+    int rc = plan_scan(ix, k, 1, &g, words, 4, words, ix->n_codes);
+    if (rc) return rc;
+    rc = ensure_parts(c, (size_t)g.grid * k); if (rc) return rc;
+    {
+        size_t need = (size_t)g.grid * k;
+        if (need > c->scan_cap) {
+            size_t c0 = c->scan_cap, c1 = c->scan_cap;
+            rc = ensure(&c->d_scan[0], &c0, need); if (rc) return rc;
+            rc = ensure(&c->d_scan[1], &c1, need); if (rc) return rc;
+            c->scan_cap = c0 < c1 ? c0 : c1;
+        }
+    }
+    g.pdl = 0;
+    ScanParams p = map_params(ix);
+    p.rows = ix->d_codes; p.norms = reinterpret_cast<const float*>(ix->d_inorms); p.queries = reinterpret_cast<const float*>(d_q8);
+    p.partials = c->d_scan[0]; p.n_rows = ix->n_codes; p.d = words; p.ld = words; p.row_words = g.row_words; p.tile_rows = g.tile_rows;
+    p.stages = g.stages; p.active_groups = g.groups; p.k = k; p.cand_cap = g.cand_cap; p.sync_interval = g.sync_interval; p.use_l2_hint = ix->opt_l2_hint;
+    p.i8_q_norm = d_qn; p.i8_q_sum = d_qs; p.i8_tie_mode = tie_mode; p.i8_tie_vstar = vstar;
+    p.trace = nullptr; p.early_trigger = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ix->opt_timing) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
+    rc = launch_scan_t<uint32_t, METRIC_I8, 1>(p, g, st);
+    if (rc) return rc;
+    ix->launches++;
+    if (ix->opt_timing) {
+        CUDA_TRY(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(ix->ev_mu);
+        ix->timed.push_back({e0, e1, 0});
+    }
+    const uint32_t grid = g.grid;
+    cudaError_t e = cudaSuccess;
+    {
+        size_t oc = c->out_cap, oc2 = c->out_cap;
+        rc = ensure(&c->d_rows, &oc, (size_t)k); if (rc) return rc;
+        rc = ensure(&c->d_scores, &oc2, (size_t)k); if (rc) return rc;
+        c->out_cap = oc < oc2 ? oc : oc2;
+        rc = ensure(&c->d_counts, &c->cnt_cap, 4); if (rc) return rc;
+    }
+    rc = merge_lists(ix, c, c->d_scan[0], 1, grid, k, 0, nullptr, c->d_rows, c->d_scores, c->d_counts, st, (size_t)grid * k, k);
+    if (rc) return rc;
+    rows->assign(k, 0); scores->assign(k, 0.0f);
+    uint32_t cnt = 0;
+    e = cudaMemcpyAsync(rows->data(), c->d_rows, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores->data(), c->d_scores, k * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, c->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(CGVEC_ERR_CUDA, "int8 search failed: %s", cudaGetErrorString(e));
+    rows->resize(cnt); scores->resize(cnt);
+    *cnt_out = cnt;
+    return CGVEC_OK;
+}
+
+// Row index of the `limit`-th row with a non-zero int8 norm (the last row of search_optimized's initial fill), or ~0 if the
+// index holds fewer such rows.
+static int i8_initial_fill_end(Index* ix, uint32_t limit, uint64_t* out) {
+    {
+        std::lock_guard<std::mutex> lk(ix->i8_mu);
+        auto it = ix->i8_fill_end.find(limit);
+        if (it != ix->i8_fill_end.end()) { *out = it->second; return CGVEC_OK; }
+    }
+    *out = ~0ull;
+    uint64_t seen = 0, pos = 0;
+    std::vector<int32_t> buf;
+    while (pos < ix->n_codes) {
+        const uint64_t m = std::min<uint64_t>(ix->n_codes - pos, (uint64_t)limit + 4096);
+        buf.resize(m);
+        CUDA_TRY(cudaMemcpy(buf.data(), ix->d_inorms + pos, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < m && *out == ~0ull; ++i)
+            if (buf[i] != 0 && ++seen == limit) *out = pos + i;
+        if (*out != ~0ull) break;
+        pos += m;
+    }
+    std::lock_guard<std::mutex> lk(ix->i8_mu);
+    ix->i8_fill_end[limit] = *out;
+    return CGVEC_OK;
+}
+
 CGVEC_EXPORT int cgvec_search_i8(const cgvec_index* cix, const float* query, uint32_t limit, uint64_t* out_rows, float* out_scores,
                                  uint32_t* out_count) {
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !query) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     if (out_count) *out_count = 0;
-    uint32_t k = limit < 1 ? 1 : limit;                         // optimization.rs:64 `_limit.max(1)`
+    const uint32_t k = limit < 1 ? 1 : limit;                   // optimization.rs:64 `_limit.max(1)`
     if (ix->n_codes == 0) return CGVEC_OK;                       // :70-72 empty -> empty
-    if (k > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "limit = %u exceeds the fused top-k limit of %u", k, kMaxK);
+    if (k + 1 > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "limit = %u exceeds the fused top-k limit of %u", k, kMaxK - 1);
     CUDA_TRY(cudaSetDevice(ix->device));
     SearchCtx* c = nullptr;
     int rc = ctx_acquire(ix, &c);
     if (rc) return rc;
     auto done = [&](int code) { ctx_release(ix, c); return code; };
     cudaStream_t st = c->stream;
+    cudaStreamWaitEvent(st, c->done, 0);
     const uint32_t ld8 = ix->ld8;
     rc = ensure(&c->d_q, &c->q_cap, (size_t)ix->dim + ld8 / 4 + 16); if (rc) return done(rc);
     int8_t* d_q8 = reinterpret_cast<int8_t*>(c->d_q + ((ix->dim + 3) & ~3u));
@@ -950,54 +1062,61 @@ CGVEC_EXPORT int cgvec_search_i8(const cgvec_index* cix, const float* query, uin
     if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e)));
     quantize_query_i8_kernel<<<1, 256, 0, st>>>(c->d_q, ix->dim, ld8, d_q8, d_qn, d_qs);
     ix->launches++;
-    const uint32_t sync = 8, rows_per_iter = (kI8Threads / 32) * kI8RowsPerWarp;
-    uint32_t cand = next_pow2(k + sync * rows_per_iter);
-    if (cand < 64) cand = 64;
-    const uint64_t groups = (ix->n_codes + rows_per_iter - 1) / rows_per_iter;
-    uint32_t grid = (uint32_t)ix->sm_count * 4;
-    if (groups < grid) grid = (uint32_t)groups;
-    rc = ensure_parts(c, (size_t)grid * k); if (rc) return done(rc);
-    {
-        size_t need = (size_t)grid * k;
-        if (need > c->scan_cap) {
-            size_t c0 = c->scan_cap, c1 = c->scan_cap;
-            rc = ensure(&c->d_scan[0], &c0, need); if (rc) return done(rc);
-            rc = ensure(&c->d_scan[1], &c1, need); if (rc) return done(rc);
-            c->scan_cap = c0 < c1 ? c0 : c1;
-        }
-    }
-    I8Params p{};
-    p.codes = ix->d_codes; p.norms = ix->d_inorms; p.q = d_q8; p.q_norm = d_qn; p.q_sum = d_qs; p.partials = c->d_scan[0];
-    p.n_rows = ix->n_codes; p.ld8 = ld8; p.k = k; p.cand_cap = cand; p.sync_interval = sync;
-    const size_t smem = ((ld8 + 15) & ~15u) + (size_t)cand * 8;
-    rc = ensure_smem_attr(scan_i8_kernel, 96 * 1024); if (rc) return done(rc);
-    scan_i8_kernel<<<grid, kI8Threads, smem, st>>>(p);
-    ix->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "scan_i8 launch failed: %s", cudaGetErrorString(e)));
-    {
-        size_t oc = c->out_cap, oc2 = c->out_cap;
-        rc = ensure(&c->d_rows, &oc, (size_t)k); if (rc) return done(rc);
-        rc = ensure(&c->d_scores, &oc2, (size_t)k); if (rc) return done(rc);
-        c->out_cap = oc < oc2 ? oc : oc2;
-        rc = ensure(&c->d_counts, &c->cnt_cap, 4); if (rc) return done(rc);
-    }
-    rc = merge_lists(ix, c, c->d_scan[0], 1, grid, k, 0, nullptr, c->d_rows, c->d_scores, c->d_counts, st, (size_t)grid * k, k);
+
+    // Pass 1: the k + 1 best rows under (score, lower row).  That settles everything unless the (k+1)-th score TIES with the
+    // k-th: search_optimized (:139-149) keeps a running list with strict `>` replacement of its first element and stable sorts,
+    // so which of several equal boundary scores it ends up holding, and the order among equal scores, depend on arrival order.
+    // Its outcome has a closed form (validated against the sequential restatement in oracle/ on tie-heavy inputs):
+    //   I      = the first k rows with a non-zero norm (the initial fill)
+    //   v*     = k-th best score;  A = rows with score > v*;  T = k-th lowest row among those with score >= v*
+    //   B      = rows with score == v* and row <= T, in list order: non-initial rows by DESCENDING row, then initial rows ascending
+    //   result = A  U  B minus its first P entries, P = #{a in A : a > T}
+    //   order  = score descending; equal scores: non-initial rows by descending row first, then initial rows ascending.
+    std::vector<uint64_t> r1, r2;
+    std::vector<float> s1, s2;
+    uint32_t c1 = 0, c2 = 0;
+    rc = i8_pass(ix, c, d_q8, d_qn, d_qs, k + 1, 0, 0.0f, st, &r1, &s1, &c1);
     if (rc) return done(rc);
-    std::vector<uint64_t> rows(k);
-    std::vector<float> scores(k);
-    uint32_t cnt = 0;
-    e = cudaMemcpyAsync(rows.data(), c->d_rows, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(scores.data(), c->d_scores, k * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, c->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return done(fail(CGVEC_ERR_CUDA, "int8 search failed: %s", cudaGetErrorString(e)));
     float qn = 0.0f;
     cudaMemcpy(&qn, d_qn, sizeof(float), cudaMemcpyDeviceToHost);
-    if (qn == 0.0f) cnt = 0;                                      // optimization.rs:113-115: zero query -> empty
-    for (uint32_t i = 0; i < cnt; ++i) { if (out_rows) out_rows[i] = rows[i]; if (out_scores) out_scores[i] = scores[i]; }
-    if (out_count) *out_count = cnt;
     ix->searches++;
+    if (qn == 0.0f || c1 == 0) return done(CGVEC_OK);            // optimization.rs:113-115: zero query -> empty
+    uint64_t init_end = ~0ull;
+    rc = i8_initial_fill_end(ix, k, &init_end);
+    if (rc) return done(rc);
+    auto initial = [&](uint64_t row) { return init_end == ~0ull || row <= init_end; };
+    struct Hit { uint64_t row; float score; };
+    std::vector<Hit> keep;
+    if (c1 <= k || s1[k] < s1[k - 1]) {                          // no tie across the boundary: the k best are the result set
+        for (uint32_t i = 0; i < c1 && i < k; ++i) keep.push_back({r1[i], s1[i]});
+    } else {
+        const float vstar = s1[k - 1];
+        rc = i8_pass(ix, c, d_q8, d_qn, d_qs, k, 1, vstar, st, &r2, &s2, &c2);     // the k lowest rows with score >= v*
+        if (rc) return done(rc);
+        std::vector<Hit> A;
+        for (uint32_t i = 0; i < c1; ++i) if (s1[i] > vstar) A.push_back({r1[i], s1[i]});
+        uint64_t T = 0;
+        for (uint64_t r : r2) T = std::max(T, r);
+        auto in_A = [&](uint64_t row) { for (auto& a : A) if (a.row == row) return true; return false; };
+        std::vector<uint64_t> B_rep, B_init;
+        for (uint64_t r : r2) if (!in_A(r)) (initial(r) ? B_init : B_rep).push_back(r);
+        std::sort(B_rep.begin(), B_rep.end(), std::greater<uint64_t>());
+        std::sort(B_init.begin(), B_init.end());
+        std::vector<uint64_t> B(B_rep);
+        B.insert(B.end(), B_init.begin(), B_init.end());
+        size_t P = 0;
+        for (auto& a : A) if (a.row > T) ++P;
+        keep = A;
+        for (size_t i = P; i < B.size(); ++i) keep.push_back({B[i], vstar});
+    }
+    std::sort(keep.begin(), keep.end(), [&](const Hit& x, const Hit& y) {
+        if (x.score != y.score) return x.score > y.score;
+        const bool xi = initial(x.row), yi = initial(y.row);
+        if (xi != yi) return !xi;                                // rows that entered by replacement sit in front of the initial fill
+        return xi ? x.row < y.row : x.row > y.row;
+    });
+    for (size_t i = 0; i < keep.size(); ++i) { if (out_rows) out_rows[i] = keep[i].row; if (out_scores) out_scores[i] = keep[i].score; }
+    if (out_count) *out_count = (uint32_t)keep.size();
     return done(CGVEC_OK);
 }
 
@@ -1208,6 +1327,7 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
         if (!value && ix->d_trace) { cudaFree(ix->d_trace); ix->d_trace = nullptr; }
     }
     else if (k == "p2p") ix->opt_p2p = (int)value;
+    else if (k == "xchg_timeout_ms") ix->opt_xchg_timeout_ms = (int)value;
     else if (k == "tc_min_batch") ix->opt_tc_min_nq = (int)value;
     else if (k == "tc_stages") ix->opt_tc_stages = (int)value;
     else if (k == "tc_kbs") ix->opt_tc_kbs = (int)value;

@@ -9,7 +9,7 @@
 
 namespace cgv {
 
-enum : int { METRIC_COSINE = 0, METRIC_DOT = 1, METRIC_L2 = 2 };
+enum : int { METRIC_COSINE = 0, METRIC_DOT = 1, METRIC_L2 = 2, METRIC_I8 = 3 };   // I8: the int8 cosine of search_optimized (optimization.rs:119-137)
 enum : int { FORM_SIMD = 0, FORM_SCALAR = 1, FORM_SEQ = 2, FORM_BASELINE = 3 };
 
 // ---------------------------------------------------------------------------------------------

@@ -35,6 +35,8 @@ struct XchgParams {
     float* out_scores;
     uint32_t* out_counts;
     uint64_t* trace;
+    uint32_t* err;                 // host-mapped error word of the index: set to 1 + source rank when that rank's list never arrived
+    uint64_t timeout_ns;           // bound on the flag spin (%globaltimer): a dead or absent rank becomes CGVEC_ERR_NCCL, not a hang
 };
 
 __device__ __forceinline__ uint32_t* xchg_flags(uint8_t* base) { return reinterpret_cast<uint32_t*>(base); }
@@ -81,7 +83,13 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_merge_kernel(const XchgPara
     // ---- 2. wait for every source's list of this step
     if (tid < p.world) {
         const uint32_t* f = &xchg_flags(p.peer[p.rank])[tid * kXchgMaxQ + q];
+        const uint64_t t0 = global_ns();
+        uint32_t spins = 0;
         while ((int32_t)(ld_acquire_sys(f) - p.seq) < 0) {
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > p.timeout_ns) {
+                if (p.err) atomicExch_system(p.err, 1u + tid);
+                break;
+            }
         }
     }
     __syncthreads();

@@ -2,8 +2,11 @@
 // scan planning (plan_scan), K1 launch, multi-level merge (merge_lists), the NCCL / fused peer-memory exchange and the
 // per-batch drivers local_exact / scan_batch.
 // ---- scan planning / launch ---------------------------------------------------------------------
-int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
-    g->row_words = scan_row_words(ix->ld, ix->esize);
+// `ld`, `esize`, `dim`, `n` default to the index's own matrix; the int8 scan passes its code matrix (words of 4 codes).
+int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g, uint32_t ld = 0, uint32_t esize = 0, uint32_t dim = 0, uint64_t n = ~0ull) {
+    if (ld == 0) { ld = ix->ld; esize = ix->esize; dim = ix->dim; }
+    if (n == ~0ull) n = ix->n;
+    g->row_words = scan_row_words(ld, esize);
     const uint32_t try_tiles[4] = {16, 32, 8, 4};
     uint32_t best_bytes = 0;
     for (int t = 0; t < 4; ++t) {
@@ -21,7 +24,7 @@ int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
             sync = ((sync + groups - 1) / groups) * groups;
             uint32_t cand = next_pow2(k + sync * tile);
             if (cand < 64) cand = 64;
-            ScanSmemLayout L = scan_smem_layout(g->row_words, tile, s, ix->dim, nq, cand);
+            ScanSmemLayout L = scan_smem_layout(g->row_words, tile, s, dim, nq, cand);
             if (L.total > kSmemBudget) continue;
             uint32_t bytes = s * tile * g->row_words * 4;
             if (bytes > best_bytes + best_bytes / 8) {          // keep the first (preferred) tile unless another buffers >12% more
@@ -33,7 +36,7 @@ int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g) {
         if (ix->opt_tile_rows) break;
     }
     if (!best_bytes) return fail(CGVEC_ERR_UNSUPPORTED, "dimension %u (k=%u, nq=%u) does not fit the scan kernel's shared memory", ix->dim, k, nq);
-    uint64_t tiles = (ix->n + g->tile_rows - 1) / g->tile_rows;
+    uint64_t tiles = (n + g->tile_rows - 1) / g->tile_rows;
     uint32_t grid = ix->opt_grid ? (uint32_t)ix->opt_grid : (uint32_t)ix->sm_count;
     g->grid = (uint32_t)(tiles < grid ? tiles : grid);
     if (g->grid == 0) g->grid = 1;
@@ -104,19 +107,10 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         int arc = ensure_smem_attr(merge_topk_kernel, kMergeMaxKeys * 8);
         if (arc) return arc;
     }
-    // the kernel reads list l of query q at in + (q*n_lists + l)*k: repack when the caller's layout differs
     const uint64_t* cur = in;
     uint32_t cur_lists = lists;
     int pp = 0;
-    if (!(q_stride == (size_t)lists * list_len && l_stride == list_len)) {
-        // gathered layout [list][nq][len] -> [nq][list][len] with strided 2D copies (device to device)
-        uint64_t* dst = c->d_part[0];
-        for (uint32_t q = 0; q < nq; ++q)
-            CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)q * lists * list_len, (size_t)list_len * 8, in + q * q_stride, l_stride * 8,
-                                       (size_t)list_len * 8, lists, cudaMemcpyDeviceToDevice, st));
-        cur = dst;
-        pp = 1;
-    }
+    uint64_t qs = q_stride, ls = l_stride;                       // the kernel reads strided input directly (no re-packing copies)
     while (true) {
         uint32_t per_cta_max = (kMergeMaxKeys - 8 * kTournamentMaxK) / list_len < 2 ? 2 : (kMergeMaxKeys - 8 * kTournamentMaxK) / list_len;
         if (per_cta_max > 256) per_cta_max = 256;
@@ -139,7 +133,7 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
             cfg.attrs = attr; cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_topk_kernel, cur, cur_lists, list_len, k, per_cta, sort_n, out, ascending,
                                         last ? d_rows : (uint64_t*)nullptr, last ? d_scores : (float*)nullptr, last ? d_counts : (uint32_t*)nullptr,
-                                        sorted_in, trace_slot(ix, 2)));
+                                        sorted_in, trace_slot(ix, 2), qs, ls));
         }
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -148,6 +142,7 @@ int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32
         cur_lists = n_out;
         list_len = k;
         sorted_in = 1;
+        qs = (uint64_t)n_out * k; ls = k;                        // intermediate levels are dense [nq][n_out][k]
         pp ^= 1;
     }
     return CGVEC_OK;
@@ -262,6 +257,7 @@ int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t 
             for (int r = 0; r < ix->world; ++r) xp.peer[r] = ix->xpeer[r];
             xp.out_rows = d_rows; xp.out_scores = d_scores; xp.out_counts = d_counts;
             xp.trace = trace_slot(ix, 3);
+            xp.err = ix->h_xerr; xp.timeout_ns = (uint64_t)(ix->opt_xchg_timeout_ms > 0 ? ix->opt_xchg_timeout_ms : 5000) * 1000000ull;
             const size_t smem = ((size_t)lists * k + 9 * k) * 8;
             {
                 cudaLaunchConfig_t cfg{};

@@ -104,7 +104,7 @@ uint32_t tc_batch_limit(const Index* ix, uint32_t nq) {
 // ordering on tcgen05, exact re-score of the kp survivors per query, proof of exactness; unproven queries are
 // re-run on the exact-order kernel.  Produces this shard's exact best-k keys (`local_keys` [nq][k]) or decoded results.
 int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
-                 uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+                 uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, int formula = CGVEC_FORMULA_SIMD) {
     {
         int arc = ensure_smem_attr(tc_scan_kernel, kSmemBudget);
         if (!arc) arc = ensure_smem_attr(tc2_scan_kernel, kSmemBudget);
@@ -230,10 +230,10 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
         const uint32_t total = nq * kp;
         if (f32)
             tc_rescore_kernel<float><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
-                                                                             ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, ix->row_offset, c->d_exact);
+                                                                             ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, formula, ix->row_offset, c->d_exact);
         else
             tc_rescore_kernel<__half><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
-                                                                              ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, ix->row_offset, c->d_exact);
+                                                                              ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, formula, ix->row_offset, c->d_exact);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -248,7 +248,8 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     //   rho_q            query rounding to the operand type, measured per query (Cauchy-Schwarz), added in the kernel
     //   2^-10 (+ cross)  TF32 only: the tensor core drops 13 mantissa bits of the ROWS as well
     const float acc_bound = (float)(ix->dim + 8) * 1.1920929e-7f + (float)(ix->dim / 8 + 12) * 5.9604645e-8f +
-                            2.0f * (float)(ix->dim / 8 + 16) * 5.9604645e-8f + (f32 ? 1.0e-3f : 0.0f);
+                            2.0f * (float)(ix->dim / 8 + 16) * 5.9604645e-8f + (f32 ? 1.0e-3f : 0.0f) +
+                            (formula != CGVEC_FORMULA_SIMD ? 4.0f * (float)(ix->dim + 8) * 5.9604645e-8f : 0.0f);   // |formula(x) - simd(x)| (search_formula's eps)
     tc_verify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c->d_cand, kTcCap, d_cnt, kp, sorted, want ? want : 1, d_na, d_rho, acc_bound, METRIC_COSINE, nq,
                                                       d_proven, d_overflow);
     ix->launches++;
@@ -261,16 +262,19 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     for (uint32_t q = 0; q < nq; ++q) {
         if (c->h_proven[q]) continue;
         ix->tc_fallbacks++;                      // could not prove: this query takes the exact-order kernel
-        rc = local_exact(ix, c, d_q + (size_t)q * qstride, 1, k, CGVEC_COSINE, st, local_keys ? local_keys + (size_t)q * k : nullptr,
-                         d_rows ? d_rows + (size_t)q * k : nullptr, d_scores ? d_scores + (size_t)q * k : nullptr, d_counts ? d_counts + q : nullptr);
+        if (formula != CGVEC_FORMULA_SIMD)       // (host-I/O, unsharded only: outputs are the pinned host mirrors)
+            rc = search_formula(ix, c, d_q + (size_t)q * qstride, k, formula, st, d_rows + (size_t)q * k, d_scores + (size_t)q * k, d_counts + q);
+        else
+            rc = local_exact(ix, c, d_q + (size_t)q * qstride, 1, k, CGVEC_COSINE, st, local_keys ? local_keys + (size_t)q * k : nullptr,
+                             d_rows ? d_rows + (size_t)q * k : nullptr, d_scores ? d_scores + (size_t)q * k : nullptr, d_counts ? d_counts + q : nullptr);
         if (rc) return rc;
     }
     return CGVEC_OK;
 }
 
 int tensor_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
-                 uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
-    if (ix->world == 1) return local_tensor(ix, c, d_q, qstride, nq, k, st, nullptr, d_rows, d_scores, d_counts);
+                 uint64_t* d_rows, float* d_scores, uint32_t* d_counts, int formula = CGVEC_FORMULA_SIMD) {
+    if (ix->world == 1) return local_tensor(ix, c, d_q, qstride, nq, k, st, nullptr, d_rows, d_scores, d_counts, formula);
     uint64_t* local_keys = nullptr;
     int rc = ensure_gather(ix, c, nq, k, &local_keys);
     if (rc) return rc;
@@ -279,16 +283,21 @@ int tensor_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     return exchange_and_decode(ix, c, local_keys, nq, k, 0, st, d_rows, d_scores, d_counts);
 }
 
+// AUTO's rule for sending a batch to the tensor kernels (rank-invariant on a sharded index).
+bool tensor_auto_ok(const Index* ix, int metric, uint32_t nq, uint32_t k) {
+    const uint32_t min_nq = ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq;
+    return tensor_path_applicable(ix, metric, nq) && nq >= min_nq && (ix->world > 1 ? ix->agreed_min_n : ix->n) >= 4 * kTcCap && k <= kTcCap / 16;
+}
+
 // Runs nq queries (device, stride qstride) through whichever kernel family `path` selects, in batches.
 int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, int metric, int path, cudaStream_t st,
-                uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+                uint64_t* d_rows, float* d_scores, uint32_t* d_counts, int formula = CGVEC_FORMULA_SIMD) {
     bool tensor = false;
     if (path == CGVEC_PATH_TENSOR) {
         if (!tensor_path_applicable(ix, metric, nq)) return fail(CGVEC_ERR_UNSUPPORTED, "the tensor-core path serves the cosine metric");
         tensor = true;
     } else if (path == CGVEC_PATH_AUTO) {
-        const uint32_t min_nq = ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq;
-        tensor = tensor_path_applicable(ix, metric, nq) && nq >= min_nq && (ix->world > 1 ? ix->agreed_min_n : ix->n) >= 4 * kTcCap && k <= kTcCap / 16;   // rank-invariant
+        tensor = tensor_auto_ok(ix, metric, nq, k);
     }
     uint32_t n_max = tensor ? tc_batch_limit(ix, nq) : 0;
     if (tensor && n_max == 0) {
@@ -302,7 +311,7 @@ int run_queries(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uin
         if (tensor) {
             b = nq - q0 < n_max ? nq - q0 : n_max;
             rc = tensor_batch(ix, c, d_q + (size_t)q0 * qstride, qstride, b, k, st, d_rows ? d_rows + (size_t)q0 * k : nullptr,
-                              d_scores ? d_scores + (size_t)q0 * k : nullptr, d_counts ? d_counts + q0 : nullptr);
+                              d_scores ? d_scores + (size_t)q0 * k : nullptr, d_counts ? d_counts + q0 : nullptr, formula);
         } else {
             b = nq - q0 >= 4 && ix->opt_max_nq >= 4 ? 4 : (nq - q0 >= 2 && ix->opt_max_nq >= 2 ? 2 : 1);
             rc = scan_batch(ix, c, d_q + (size_t)q0 * qstride, b, k, metric, st, d_rows ? d_rows + (size_t)q0 * k : nullptr,

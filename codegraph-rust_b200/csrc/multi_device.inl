@@ -72,6 +72,9 @@ int multi_create(uint32_t dim, cgvec_dtype storage, const int* device_ids, int n
     }
     mx->device = mx->parts[0]->device;
     mx->sm_count = mx->parts[0]->sm_count;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&mx->h_xerr), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+        return cleanup(fail(CGVEC_ERR_OOM, "pinned error word"));
+    *mx->h_xerr = 0;
     *out = mx.release();
     return CGVEC_OK;
 }
@@ -86,6 +89,7 @@ void multi_destroy(Index* mx) {
         if (p->main_stream) cudaStreamDestroy(p->main_stream);
         delete static_cast<cgvec_index*>(p);
     }
+    cudaFreeHost(mx->h_xerr);
     delete static_cast<cgvec_index*>(mx);
 }
 
@@ -285,6 +289,7 @@ int multi_search(Index* mx, const float* queries, uint32_t nq, uint32_t k, const
             xp.partials = partials; xp.n_lists = lists; xp.k = k; xp.nq = b; xp.ascending = (o.metric == CGVEC_L2);
             xp.rank = (uint32_t)s; xp.world = (uint32_t)G; xp.seq = seq;
             for (size_t r = 0; r < G; ++r) xp.peer[r] = p->xpeer[r];
+            xp.err = mx->h_xerr; xp.timeout_ns = (uint64_t)(mx->opt_xchg_timeout_ms > 0 ? mx->opt_xchg_timeout_ms : 5000) * 1000000ull;
             if (s == 0) { xp.out_rows = c0->d_rows + (size_t)q0 * k; xp.out_scores = c0->d_scores + (size_t)q0 * k; xp.out_counts = c0->d_counts + q0; }
             xchg_merge_kernel<<<b, kXchgThreads, ((size_t)lists * k + 9 * k) * 8, c->stream>>>(xp);
             p->launches++;
@@ -298,6 +303,7 @@ int multi_search(Index* mx, const float* queries, uint32_t nq, uint32_t k, const
     if (e == cudaSuccess) e = cudaMemcpyAsync(c0->h_counts, c0->d_counts, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, c0->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c0->stream);
     if (e != cudaSuccess) return finish(fail(CGVEC_ERR_CUDA, "multi-device search failed: %s", cudaGetErrorString(e)));
+    if (mx->h_xerr && *mx->h_xerr) return finish(fail(CGVEC_ERR_NCCL, "peer exchange timed out waiting for device %u", *mx->h_xerr - 1));
     for (uint32_t q = 0; q < nq; ++q) {
         const uint32_t cnt = c0->h_counts[q];
         if (out_counts) out_counts[q] = cnt;

@@ -55,6 +55,12 @@ struct ScanParams {
     // global row = ((local / blk_rows) * n_shards + shard_id) * blk_rows + local % blk_rows + row_offset
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
+    // METRIC_I8 (int8 quantised scan, scan_i8.cuh): rows are u8 codes viewed as 32-bit words, `norms` holds int32 sum((code-128)^2),
+    // `queries` the quantised query as packed s8 words; d / ld count WORDS.
+    const float* i8_q_norm;    // [1] sqrt(sum(q^2)) as the reference accumulates it
+    const int32_t* i8_q_sum;   // [1] sum(q)
+    uint32_t i8_tie_mode;      // 1: keep the k LOWEST rows with score >= i8_tie_vstar (second pass of the reference's tie resolution)
+    float i8_tie_vstar;
     uint64_t* trace;           // optional [start, end] slot of this launch (see common.cuh trace_begin)
     uint32_t early_trigger;    // PDL chain mode 2: release dependents at once, order our partial-list WRITE after the predecessor
 };
@@ -157,6 +163,32 @@ __device__ __forceinline__ void score_row_octet(const T* __restrict__ row, const
     }
 }
 
+// int8 cosine numerator of one row (search_optimized, optimization.rs:124-130): sum((code - 128) * q) over the row, computed as
+// dp4a.u32.s32(codes, q) - 128 * sum(q) by the caller.  Integer arithmetic is associative, so no order has to be reproduced:
+// thread L takes words L, L+8, ... and the octet is reduced with shuffles.  Valid on octet lane 0.
+__device__ __forceinline__ int i8_dot_octet(const uint32_t* __restrict__ row, const uint32_t* __restrict__ q, uint32_t words, int L) {
+    int acc0 = 0, acc1 = 0;
+    uint32_t i = L;
+    // 8 row words + 8 query words in flight per thread before the first dp4a: at 1 byte per element the scan needs four times
+    // the rows per second of the f32 scan from the same 8 consumer warps, so the loads must not wait for each other
+    for (; i + 56 < words; i += 64) {
+        uint32_t a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a[u] = row[i + 8 * u]; b[u] = q[i + 8 * u]; }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc0) : "r"(a[u]), "r"(b[u]));
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc1) : "r"(a[u + 1]), "r"(b[u + 1]));
+        }
+    }
+    for (; i < words; i += 8) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc0) : "r"(row[i]), "r"(q[i]));
+    int acc = acc0 + acc1;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    return acc;
+}
+
 // Squared norm of a vector held in shared/global memory, in the order the cosine kernels above imply
 // (AVX2 lanes + hsum + tail for d >= 32, sequential un-fused below).  Valid on octet lane 0.
 template <typename T>
@@ -240,7 +272,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
             const uint64_t tile = blockIdx.x + n * gridDim.x;
             const uint64_t row0 = tile * p.tile_rows;
             const uint32_t rows = (uint32_t)min((uint64_t)p.tile_rows, p.n_rows - row0);
-            const bool with_norms = (METRIC == METRIC_COSINE);
+            const bool with_norms = (METRIC == METRIC_COSINE || METRIC == METRIC_I8);
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes + (with_norms ? p.tile_rows * 4 : 0));
             __syncwarp();
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rows) + row0 * row_bytes;
@@ -260,6 +292,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
         const uint32_t lrow = sub * 4 + (lane >> 3);             // row of the tile this octet scores
 
         mbar_wait(q_bar, 0);
+        float i8_qnorm = 0.0f;
+        int i8_qsum = 0;
+        if constexpr (METRIC == METRIC_I8) { i8_qnorm = *p.i8_q_norm; i8_qsum = *p.i8_q_sum; }
         float na[NQ];
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
@@ -302,12 +337,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(const ScanP
             const uint64_t tile = blockIdx.x + n * gridDim.x;
             const uint64_t row = tile * p.tile_rows + lrow;      // local row index
             const T* rp = reinterpret_cast<const T*>(s_rows + (size_t)s * stage_bytes + (size_t)lrow * p.row_words * 4);
-            const float nb = (METRIC == METRIC_COSINE) ? s_norms[s * 32 + lrow] : 0.0f;
+            const float nb = (METRIC == METRIC_COSINE || METRIC == METRIC_I8) ? s_norms[s * 32 + lrow] : 0.0f;
             float sc[NQ];
-            score_row_octet<T, METRIC, NQ>(rp, s_q, qstride, p.d, L, na, nb, sc);
+            bool skip = false;
+            if constexpr (METRIC == METRIC_I8) {
+                const int s1 = i8_dot_octet(reinterpret_cast<const uint32_t*>(rp), reinterpret_cast<const uint32_t*>(s_q), p.d, L);
+                const int nv = __float_as_int(nb);
+                skip = nv == 0;                                                     // optimization.rs:132-134
+                const int dot = s1 - 128 * i8_qsum;
+                sc[0] = skip ? 0.0f : div_rn((float)dot, mul_rn(i8_qnorm, sqrt_rn((float)nv)));   // :136
+                if (p.i8_tie_mode) { skip = skip || !(sc[0] >= p.i8_tie_vstar); sc[0] = 1.0f; }
+            } else {
+                score_row_octet<T, METRIC, NQ>(rp, s_q, qstride, p.d, L, na, nb, sc);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);           // stage may be refilled
-            if (L == 0 && row < p.n_rows) {
+            if (L == 0 && row < p.n_rows && !skip) {
                 const uint32_t grow = (uint32_t)scan_global_row(p, row);
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {

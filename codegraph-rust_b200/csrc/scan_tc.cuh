@@ -783,11 +783,13 @@ __global__ void tc_prep_queries_kernel(const float* __restrict__ q, uint32_t qst
     if (octet == 0 && L == 0) *overflow = 0;
 }
 
-// ---- exact re-scoring of the survivors (K4, batched): keys_in[q][i] (approx) -> keys_out[q][i] (exact SIMD-order score) ----
+// ---- exact re-scoring of the survivors (K4, batched): keys_in[q][i] (approx) -> keys_out[q][i] (exact score in `formula`) ----
+// FORM_SIMD: adaptive_cosine_similarity order (one octet per pair).  FORM_SCALAR / FORM_SEQ: the reference's sequential
+// cosines (simd_ops.rs:262-277, search.rs:524-532), inherently serial, run on octet lane 0.
 template <typename T>
 __global__ void tc_rescore_kernel(const T* __restrict__ rows, uint32_t d, uint32_t ld, const float* __restrict__ q, uint32_t qstride,
                                   const float* __restrict__ na, const float* __restrict__ norms, const uint64_t* __restrict__ keys_in,
-                                  uint32_t cap, uint32_t kp, uint32_t nq, int metric, uint64_t row_offset,
+                                  uint32_t cap, uint32_t kp, uint32_t nq, int metric, int formula, uint64_t row_offset,
                                   uint64_t* __restrict__ keys_out) {
     const uint32_t octet = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int L = threadIdx.x & 7;
@@ -801,10 +803,31 @@ __global__ void tc_rescore_kernel(const T* __restrict__ rows, uint32_t d, uint32
     const T* row = rows + lrow * ld;
     const float* qv = q + (size_t)qi * qstride;
     float res = 0.0f;
-    const float naq = na[qi];
-    const float nb = (metric == METRIC_COSINE) ? norms[lrow] : 0.0f;
-    if (metric == METRIC_COSINE) score_row_octet<T, METRIC_COSINE, 1>(row, qv, 0, d, L, &naq, nb, &res);
-    else score_row_octet<T, METRIC_DOT, 1>(row, qv, 0, d, L, &naq, nb, &res);
+    if (formula == FORM_SIMD) {
+        const float naq = na[qi];
+        const float nb = (metric == METRIC_COSINE) ? norms[lrow] : 0.0f;
+        if (metric == METRIC_COSINE) score_row_octet<T, METRIC_COSINE, 1>(row, qv, 0, d, L, &naq, nb, &res);
+        else score_row_octet<T, METRIC_DOT, 1>(row, qv, 0, d, L, &naq, nb, &res);
+    } else if (L == 0 && present) {
+        float dp = 0.0f, sa = 0.0f, sb = 0.0f;
+        if (formula == FORM_SCALAR) {                            // simd_ops.rs:262-277 (one interleaved loop)
+            for (uint32_t i = 0; i < d; ++i) {
+                const float va = qv[i], vb = ldf(row + i);
+                dp = add_rn(dp, mul_rn(va, vb));
+                sa = add_rn(sa, mul_rn(va, va));
+                sb = add_rn(sb, mul_rn(vb, vb));
+            }
+            const float np = sqrt_rn(mul_rn(sa, sb));
+            res = (np == 0.0f) ? 0.0f : div_rn(dp, np);
+        } else {                                                 // search.rs:524-532
+            for (uint32_t i = 0; i < d; ++i) dp = add_rn(dp, mul_rn(qv[i], ldf(row + i)));
+            for (uint32_t i = 0; i < d; ++i) sa = add_rn(sa, mul_rn(qv[i], qv[i]));
+            for (uint32_t i = 0; i < d; ++i) { const float vb = ldf(row + i); sb = add_rn(sb, mul_rn(vb, vb)); }
+            sa = sqrt_rn(sa);
+            sb = sqrt_rn(sb);
+            res = (sa == 0.0f || sb == 0.0f) ? 0.0f : div_rn(dp, mul_rn(sa, sb));
+        }
+    }
     if (L == 0 && octet < total) keys_out[(size_t)qi * kp + ci] = present ? make_key(res, grow, false) : 0ull;
 }
 

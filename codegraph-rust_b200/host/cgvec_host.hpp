@@ -19,6 +19,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -310,6 +311,55 @@ public:
 
 private:
     std::shared_ptr<B200VectorStore> store_;
+};
+
+// Steps 1-2 of fn::semantic_search_nodes_via_chunks (schema/codegraph.surql:318-417), the vector stage behind
+// execute_semantic_code_search (codegraph-mcp-tools/src/graph_tool_executor.rs:578-591): the 100 nearest chunk embeddings
+// (`<|100,200|>`), minus chunks without a parent node, cut to 3 x safe_limit rows (safe_limit = limit when 1 <= limit <= 100,
+// else 10), each mapped to (parent node, 1 - cosine distance).  The KNN is this library's exact scan (B200Backend::vector_knn)
+// in place of SurrealDB's approximate HNSW; BM25, the 0.9/0.1 blend and the graph enrichment stay in SurrealDB.
+struct ChunkRecord {
+    NodeId id;
+    std::optional<NodeId> parent_node;
+    std::vector<float> embedding;
+};
+struct ChunkCandidate {
+    NodeId node_id;        // <string> parent_node AS node_id (codegraph.surql:403)
+    float vector_score;    // 1f - distance (:412)
+    NodeId chunk_id;
+};
+class ChunkCandidateStage {
+public:
+    static constexpr size_t kKnn = 100;                        // the literal of `<|100,200|>`
+    explicit ChunkCandidateStage(uint32_t dimension, cgvec_dtype storage = CGVEC_F32, int device = 0)
+        : store_(std::make_shared<B200VectorStore>(dimension, storage, device)), backend_(std::make_shared<B200Backend>(store_)) {}
+    void upsert_chunks(const std::vector<ChunkRecord>& chunks) {
+        std::vector<CodeNode> nodes;
+        for (auto& c : chunks) nodes.push_back({c.id, c.embedding});
+        backend_->upsert_nodes(nodes);
+        for (auto& c : chunks) parent_[c.id.to_string()] = c.parent_node;
+    }
+    std::vector<ChunkCandidate> candidates(const std::vector<float>& query_embedding, long limit) const {
+        const size_t safe_limit = (limit > 0 && limit <= 100) ? (size_t)limit : 10;      // codegraph.surql:325
+        const size_t chunk_limit = safe_limit * 3;                                        // :326
+        auto hits = backend_->vector_knn("embedding_" + std::to_string(store_->dimension()), query_embedding, kKnn, 200);
+        std::vector<ChunkCandidate> out;
+        for (auto& [raw, distance] : hits) {
+            auto cid = NodeId::parse_str(raw.substr(raw.rfind(':') + 1));
+            if (!cid) throw Error(CGVEC_ERR_BAD_ARG, "Invalid chunk id '" + raw + "'");
+            auto it = parent_.find(cid->to_string());
+            if (it == parent_.end() || !it->second) continue;                              // parent_node != NONE
+            out.push_back({*it->second, 1.0f - distance, *cid});
+            if (out.size() == chunk_limit) break;                                          // LIMIT $chunk_limit
+        }
+        return out;
+    }
+    std::shared_ptr<B200VectorStore> store() const { return store_; }
+
+private:
+    std::shared_ptr<B200VectorStore> store_;
+    std::shared_ptr<B200Backend> backend_;
+    std::unordered_map<std::string, std::optional<NodeId>> parent_;
 };
 
 }  // namespace cgvec

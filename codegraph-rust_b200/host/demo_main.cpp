@@ -56,6 +56,20 @@ int main(int argc, char** argv) {
             for (float x : gpu.compute_distances(q, *data, 5)) std::cout << " " << std::hexfloat << x << std::defaultfloat;
             std::cout << "\n";
         }
+        {   // candidate stage of semantic_code_search: chunk i belongs to node i / 3; every 5th chunk is an orphan
+            cgvec::ChunkCandidateStage stage((uint32_t)dim);
+            std::vector<cgvec::ChunkRecord> chunks;
+            for (size_t i = 0; i < n; ++i) {
+                std::optional<cgvec::NodeId> parent;
+                if (i % 5 != 4) parent = cgvec::NodeId::from_u64(1000000 + i / 3);
+                chunks.push_back({cgvec::NodeId::from_u64(i + 1), parent, hash_text_embedding("fn item_" + std::to_string(i) + "() {}", dim)});
+            }
+            stage.upsert_chunks(chunks);
+            std::cout << "candidates";
+            for (auto& c : stage.candidates(q, (long)limit))
+                std::cout << " " << c.node_id.to_string() << "/" << c.chunk_id.to_string() << "/" << std::hexfloat << c.vector_score << std::defaultfloat;
+            std::cout << "\ncandidates_bad_limit " << stage.candidates(q, 0).size() << " " << stage.candidates(q, 1000).size() << "\n";
+        }
         auto missing = store->get_embedding(cgvec::NodeId::from_u64(123456789));
         std::cout << "missing " << (missing ? "some" : "none") << "\n";
         try {

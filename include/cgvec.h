@@ -163,8 +163,10 @@ int cgvec_distances_first(const cgvec_index* idx, const float* query, uint64_t l
 
 /* ---- int8 quantised scan: ModelOptimizer::quantize_batch + OptimizationResult::search_optimized
  * (codegraph-vector/src/optimization.rs:63-150, :212-224, :268-274).  cgvec_quantize_i8 builds u8 codes (value + 128)
- * of the currently stored rows; cgvec_search_i8 returns up to max(limit,1) rows by the int8 cosine, best first
- * (ties -> lower row), with scores bit-identical to the reference's f32 expression.  Single-GPU indexes. */
+ * of the currently stored rows; cgvec_search_i8 returns up to max(limit,1) rows by the int8 cosine, best first, with
+ * scores bit-identical to the reference's f32 expression and EXACTLY the rows and the order the reference's running list
+ * (strict `>` replacement + stable sorts, :139-149) produces, ties included.  Codes go stale on any write (quantize again).
+ * Single-GPU indexes; limit <= 1023. */
 int cgvec_quantize_i8(cgvec_index* idx);
 int cgvec_get_codes_i8(const cgvec_index* idx, uint64_t first_row, uint64_t n, uint8_t* out /* n x dim */);
 int cgvec_search_i8(const cgvec_index* idx, const float* query, uint32_t limit, uint64_t* out_rows, float* out_scores,

@@ -48,6 +48,14 @@ def test_host_mirror_matches_oracle(cg, oracle):
     flat = np.stack([oracle.hash_text_embedding(f"v{i}", dim) for i in range(20)])
     want_d = oracle.compute_distances_cpu(q, flat.reshape(-1), dim, 5)
     assert np.float32([float.fromhex(x) for x in lines["gpu_distances"].split()]).tobytes() == want_d.tobytes()
+    # candidate stage (codegraph.surql:318-417): 100 nearest chunks, orphans dropped, LIMIT 3 * safe_limit, 1 - distance
+    w100, s100 = oracle.parallel_top_k_search(q, embs, 100)
+    want_c = [(int(i), np.float32(1.0) - (np.float32(1.0) - s)) for i, s in zip(w100, s100) if int(i) % 5 != 4][: 3 * limit]
+    got_c = [t.split("/") for t in lines["candidates"].split()]
+    assert [c[1] for c in got_c] == [f"00000000-0000-0000-0000-{i + 1:012x}" for i, _ in want_c]
+    assert [c[0] for c in got_c] == [f"00000000-0000-0000-0000-{1000000 + i // 3:012x}" for i, _ in want_c]
+    assert np.float32([float.fromhex(c[2]) for c in got_c]).tobytes() == np.float32([s for _, s in want_c]).tobytes()
+    assert lines["candidates_bad_limit"].split() == ["30", "30"]                   # limit outside 1..100 -> safe_limit 10
     assert lines["missing"] == "none"
     assert lines["baddim"] == str(cg.ERR_BAD_DIM)
 

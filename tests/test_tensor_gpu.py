@@ -115,3 +115,33 @@ def test_tf32_tensor_path_for_f32_storage(cg, oracle, d, nq, k, kernel):
     """f32 rows go through kind::tf32 (both operands lose 13 mantissa bits inside the tensor core); the exact re-score
     and the wider error bound still deliver bit-exact results (BASELINE config 5's storage type)."""
     _run(cg, oracle, 60_000, d, nq, k, seed=d * 3 + nq, f32=True, opts={"tc_kernel": kernel})
+
+
+def test_symbol_resolver_dense_pass(cg, oracle):
+    """U x S cosine arg-max with threshold 0.75 (codegraph-mcp/src/indexer.rs:2827-2843) as dense tensor-core
+    passes (k = 1) with the winners re-scored in the reference's sequential cosine: U = 4096 references, S = 200k symbols."""
+    rng = np.random.default_rng(2843)
+    S, U, d = 200_000, 4096, 384
+    syms = rng.standard_normal((S, d)).astype(np.float32)
+    syms /= np.linalg.norm(syms, axis=1, keepdims=True)
+    targets = rng.standard_normal((U, d)).astype(np.float32)
+    planted = rng.choice(U, U // 2, replace=False)                       # half the references really are a known symbol + noise
+    which = rng.integers(0, S, len(planted))
+    targets[planted] = syms[which] + rng.normal(0, 0.3 / np.sqrt(d), (len(planted), d)).astype(np.float32)
+    ix = cg.Index(d, cg.F32)
+    try:
+        ix.add(syms)
+        got = cg.resolve_symbols(ix, targets, 0.75)
+        st = ix.stats()
+        assert st.tc_batches >= U // 256, "the dense path should have carried the batch"
+        assert st.tc_fallbacks <= U // 50
+        hit = {int(u): int(w) for u, w in zip(planted, which)}
+        check = list(planted[:40]) + [u for u in range(U) if u not in hit][:24]
+        for u in check:
+            wi, ws = oracle.parallel_top_k_search(targets[u], syms, 1, form=oracle.FORM_SEQ)
+            want = (int(wi[0]), float(ws[0])) if ws[0] > 0.75 else None
+            assert got[u] == want, (u, got[u], want)
+        assert all(got[u] is not None and got[u][0] == hit[u] for u in list(hit)[:500])
+        assert sum(g is None for g in got) >= U // 2 - 8               # unrelated references stay unresolved
+    finally:
+        ix.close()
