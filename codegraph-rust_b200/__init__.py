@@ -29,11 +29,11 @@ COSINE, DOT, L2 = 0, 1, 2
 FORMULA_SIMD, FORMULA_SCALAR, FORMULA_SEQ, FORMULA_BASELINE = 0, 1, 2, 3
 PATH_AUTO, PATH_EXACT, PATH_TENSOR = 0, 1, 2
 
-OK, ERR_BAD_ARG, ERR_BAD_DIM, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_NOT_FOUND, ERR_NO_DEVICE, ERR_UNSUPPORTED = (
-    0, -1, -2, -3, -4, -5, -6, -7, -8)
+OK, ERR_BAD_ARG, ERR_BAD_DIM, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_NOT_FOUND, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_DISABLED = (
+    0, -1, -2, -3, -4, -5, -6, -7, -8, -9)
 
 EXPORTS = [
-    "cgvec_create", "cgvec_create_rank", "cgvec_nccl_unique_id", "cgvec_destroy", "cgvec_reserve", "cgvec_add",
+    "cgvec_create", "cgvec_create_from_env", "cgvec_create_rank", "cgvec_nccl_unique_id", "cgvec_destroy", "cgvec_reserve", "cgvec_add",
     "cgvec_add_f16", "cgvec_normalize_rows", "cgvec_fill_synthetic", "cgvec_len", "cgvec_dim", "cgvec_search",
     "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
     "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_multi_locate", "cgvec_multi_local_count", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
@@ -62,7 +62,8 @@ class Stats(C.Structure):
                 ("smem_bytes", C.c_uint32), ("stages", C.c_uint32), ("tile_rows", C.c_uint32),
                 ("last_scan_ms", C.c_float), ("scan_ms_total", C.c_double), ("scans_timed", C.c_uint64),
                 ("tc_batches", C.c_uint64), ("tc_fallbacks", C.c_uint64), ("exchange_mode", C.c_uint32), ("reserved0", C.c_uint32),
-                ("tc_main_ms_total", C.c_double), ("tc_main_timed", C.c_uint64)]
+                ("tc_main_ms_total", C.c_double), ("tc_main_timed", C.c_uint64),
+                ("coalesced_batches", C.c_uint64), ("coalesced_queries", C.c_uint64)]
 
 
 _lib = None
@@ -84,6 +85,7 @@ def load_library(build: bool = True):
     L = C.CDLL(_build.LIB)
     vp, u64p, fp, u32p, u8p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p
     L.cgvec_create.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.cgvec_create_from_env.argtypes = [C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]
     L.cgvec_create_rank.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, C.POINTER(vp)]
     L.cgvec_nccl_unique_id.argtypes = [vp]
     L.cgvec_destroy.argtypes = [vp]
@@ -210,6 +212,17 @@ class Index:
         else:
             buf = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id else None
             _check(L.cgvec_create_rank(dim, dtype, device, rank, world, buf, row_offset, C.byref(self._h)))
+
+    @classmethod
+    def from_env(cls, dim: int, dtype: int = F32, enable_gpu: bool = False) -> "Index":
+        """cgvec_create_from_env: `enable_gpu` is PerformanceConfig.enable_gpu (config_manager.rs:362-364); CODEGRAPH_ENABLE_GPU
+        overrides it, CODEGRAPH_B200_DEVICES picks the GPUs.  Raises CgvecError(ERR_DISABLED) when the switch is off."""
+        L = load_library()
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.dim, self.dtype, self.device, self.rank, self.world, self.row_offset = dim, dtype, 0, 0, 1, 0
+        _check(L.cgvec_create_from_env(dim, dtype, 1 if enable_gpu else 0, C.byref(self._h)))
+        return self
 
     # -- lifecycle
     def close(self):

@@ -6,13 +6,17 @@
 // entry point returns CGVEC_ERR_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -176,7 +180,47 @@ struct Index {
     uint64_t scan_timed = 0, tc_main_timed = 0;
     float last_scan_ms = 0.0f;
     std::atomic<uint32_t> last_exchange{0};                   // 0 none (unsharded), 1 fused peer-memory kernel, 2 NCCL all-gather
+
+    // reader-writer exclusion between the write side (add / reserve / normalize / fill / load / quantize: may reallocate the
+    // device matrix and rehash the id map) and everything that reads them; taken by the exported entry points (RwGuard)
+    std::shared_mutex rw_mu;
+    std::atomic<int> open_streams{0};                         // cgvec_stream_* sessions keep device work in flight between calls
+
+    // group commit of concurrent batch-1 callers (coalesced_search below)
+    struct PendingSearch;
+    std::mutex co_mu;
+    std::condition_variable co_cv;
+    std::deque<PendingSearch*> co_queue;
+    bool co_leader = false;
+    int opt_coalesce = 1, opt_coalesce_max = 16;
+    std::atomic<uint64_t> co_batches{0}, co_queries{0};       // batches of >= 2 callers, callers served through them
 };
+
+// Scoped reader/writer lock of an index for one exported call.  Exported functions call each other (cgvec_get -> cgvec_get_row,
+// the multi-device parent -> its parts); a thread that already holds an index does not lock it again.
+thread_local std::vector<const void*> tl_held_indexes;
+template <typename IndexT>
+struct RwGuardT {
+    IndexT* ix; int mode = 0;                                  // 0 not taken (NULL index or nested), 1 shared, 2 exclusive
+    RwGuardT(const IndexT* cix, bool write) : ix(const_cast<IndexT*>(cix)) {
+        if (!ix) return;
+        for (const void* h : tl_held_indexes) if (h == ix) return;
+        if (write) ix->rw_mu.lock(); else ix->rw_mu.lock_shared();
+        mode = write ? 2 : 1;
+        tl_held_indexes.push_back(ix);
+    }
+    ~RwGuardT() {
+        if (!mode) return;
+        for (size_t i = tl_held_indexes.size(); i-- > 0;) if (tl_held_indexes[i] == ix) { tl_held_indexes.erase(tl_held_indexes.begin() + i); break; }
+        if (mode == 2) ix->rw_mu.unlock(); else ix->rw_mu.unlock_shared();
+    }
+    RwGuardT(const RwGuardT&) = delete;
+    RwGuardT& operator=(const RwGuardT&) = delete;
+};
+using RwGuard = RwGuardT<Index>;
+#define CGVEC_WRITE_GUARD(ix)                                                                                              \
+    RwGuard rw_guard_(ix, true);                                                                                           \
+    if ((ix) && (ix)->open_streams.load() > 0) return fail(CGVEC_ERR_UNSUPPORTED, "close the index's cgvec_stream sessions before writing to it")
 
 int check_device(int device) {
     int count = 0;
@@ -389,6 +433,59 @@ CGVEC_EXPORT int cgvec_create(uint32_t dim, cgvec_dtype storage, const int* devi
     return create_common(dim, storage, device_ids ? device_ids[0] : 0, 0, 1, nullptr, 0, out);
 }
 
+// Deployment switch: the reference's PerformanceConfig.enable_gpu (codegraph-core/src/config_manager.rs:362-364,
+// default false :419) decides whether the host wires this library in at all; CODEGRAPH_ENABLE_GPU overrides it the way the
+// reference's other CODEGRAPH_* variables override their config fields (config_manager.rs:696-811), and CODEGRAPH_B200_DEVICES
+// picks the GPUs: "all", a count ("4" -> devices 0..3) or an explicit list ("0,2,5").  Unset -> device 0.
+static bool env_truthy(const char* v, bool dflt) {
+    if (!v || !*v) return dflt;
+    std::string t(v);
+    for (auto& ch : t) ch = (char)tolower((unsigned char)ch);
+    if (t == "1" || t == "true" || t == "yes" || t == "on") return true;
+    if (t == "0" || t == "false" || t == "no" || t == "off") return false;
+    return dflt;
+}
+CGVEC_EXPORT int cgvec_create_from_env(uint32_t dim, cgvec_dtype storage, int enable_gpu, cgvec_index** out) {
+    if (!out) return fail(CGVEC_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (!env_truthy(getenv("CODEGRAPH_ENABLE_GPU"), enable_gpu != 0))
+        return fail(CGVEC_ERR_DISABLED, "GPU acceleration is switched off (performance.enable_gpu / CODEGRAPH_ENABLE_GPU)");
+    const char* spec = getenv("CODEGRAPH_B200_DEVICES");
+    std::vector<int> devs;
+    if (!spec || !*spec) devs.push_back(0);
+    else {
+        std::string t(spec);
+        for (auto& ch : t) ch = (char)tolower((unsigned char)ch);
+        if (t == "all") {
+            int n = 0;
+            if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); return fail(CGVEC_ERR_NO_DEVICE, "CODEGRAPH_B200_DEVICES=all but no CUDA device is visible"); }
+            if (n > (int)kXchgMaxWorld) n = (int)kXchgMaxWorld;
+            for (int i = 0; i < n; ++i) devs.push_back(i);
+        } else {
+            std::vector<int> vals;
+            size_t pos = 0;
+            bool list = t.find(',') != std::string::npos;
+            while (pos <= t.size()) {
+                size_t e = t.find(',', pos);
+                if (e == std::string::npos) e = t.size();
+                std::string tok = t.substr(pos, e - pos);
+                size_t a = tok.find_first_not_of(" \t"), b = tok.find_last_not_of(" \t");
+                if (a == std::string::npos) return fail(CGVEC_ERR_BAD_ARG, "CODEGRAPH_B200_DEVICES='%s': empty entry", spec);
+                tok = tok.substr(a, b - a + 1);
+                if (tok.find_first_not_of("0123456789") != std::string::npos || tok.size() > 4)
+                    return fail(CGVEC_ERR_BAD_ARG, "CODEGRAPH_B200_DEVICES='%s': '%s' is not a device number", spec, tok.c_str());
+                vals.push_back(atoi(tok.c_str()));
+                pos = e + 1;
+            }
+            if (!list) {                                         // a single number is a COUNT of devices (0..n-1)
+                if (vals[0] < 1) return fail(CGVEC_ERR_BAD_ARG, "CODEGRAPH_B200_DEVICES='%s': device count must be >= 1", spec);
+                for (int i = 0; i < vals[0]; ++i) devs.push_back(i);
+            } else devs = vals;
+        }
+    }
+    return cgvec_create(dim, storage, devs.data(), (int)devs.size(), out);
+}
+
 CGVEC_EXPORT int cgvec_create_rank(uint32_t dim, cgvec_dtype storage, int device, int rank, int world, const void* nccl_unique_id,
                                    uint64_t row_offset, cgvec_index** out) {
     return create_common(dim, storage, device, rank, world, nccl_unique_id, row_offset, out);
@@ -429,6 +526,7 @@ CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
 // write side
 // ================================================================================================
 CGVEC_EXPORT int cgvec_reserve(cgvec_index* ix, uint64_t n_rows) {
+    CGVEC_WRITE_GUARD(ix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (!ix->parts.empty()) return multi_reserve(ix, n_rows);
     CUDA_TRY(cudaSetDevice(ix->device));
@@ -436,6 +534,7 @@ CGVEC_EXPORT int cgvec_reserve(cgvec_index* ix, uint64_t n_rows) {
 }
 
 static int add_impl(cgvec_index* ix, const uint8_t (*ids)[16], const void* rows, uint64_t n, uint32_t src_esize) {
+    CGVEC_WRITE_GUARD(ix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (n == 0) return CGVEC_OK;
     if (!rows) return fail(CGVEC_ERR_BAD_ARG, "rows is NULL");
@@ -496,6 +595,7 @@ CGVEC_EXPORT int cgvec_add_f16(cgvec_index* ix, const uint8_t (*ids)[16], const 
 }
 
 CGVEC_EXPORT int cgvec_normalize_rows(cgvec_index* ix) {
+    CGVEC_WRITE_GUARD(ix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (!ix->parts.empty()) {
         for (Index* p : ix->parts) { int rc = cgvec_normalize_rows(static_cast<cgvec_index*>(p)); if (rc) return rc; }
@@ -517,6 +617,7 @@ CGVEC_EXPORT int cgvec_normalize_rows(cgvec_index* ix) {
 }
 
 CGVEC_EXPORT int cgvec_fill_synthetic(cgvec_index* ix, uint64_t n, uint64_t seed, int unit_norm) {
+    CGVEC_WRITE_GUARD(ix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (!n) return CGVEC_OK;
     if (!ix->parts.empty()) return multi_fill_synthetic(ix, n, seed, unit_norm);
@@ -558,28 +659,9 @@ CGVEC_EXPORT uint32_t cgvec_dim(const cgvec_index* ix) { return ix ? ix->dim : 0
 // formula != SIMD: over-fetch with the exact SIMD-order scan, re-score the candidates in the requested
 // formula on the device, re-rank, and PROVE no outside row can enter the top-k (else widen and retry).
 
-CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, uint32_t nq, uint32_t k,
-                                 const cgvec_search_opts* opts, uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores,
-                                 uint32_t* out_counts) {
-    Index* ix = const_cast<cgvec_index*>(cix);
-    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
-    cgvec_search_opts o{};
-    o.struct_size = sizeof(o);
-    if (opts) {
-        if (opts->struct_size < sizeof(uint32_t) * 4) return fail(CGVEC_ERR_BAD_ARG, "opts->struct_size is not set");
-        memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
-    }
-    if (o.metric != CGVEC_COSINE && o.metric != CGVEC_DOT && o.metric != CGVEC_L2) return fail(CGVEC_ERR_BAD_ARG, "unknown metric %d", (int)o.metric);
-    if (o.formula < CGVEC_FORMULA_SIMD || o.formula > CGVEC_FORMULA_BASELINE) return fail(CGVEC_ERR_BAD_ARG, "unknown formula %d", (int)o.formula);
-    if (o.formula != CGVEC_FORMULA_SIMD && o.metric != CGVEC_COSINE)
-        return fail(CGVEC_ERR_UNSUPPORTED, "formulas other than SIMD exist for cosine only (the reference has no scalar dot / L2)");
-    if (o.device_io && out_ids) return fail(CGVEC_ERR_BAD_ARG, "out_ids cannot be produced with device_io");
-    if (o.device_io && o.formula != CGVEC_FORMULA_SIMD) return fail(CGVEC_ERR_UNSUPPORTED, "device_io supports the SIMD formula only");
-    if (nq == 0 || k == 0) {                                   // surreal_store.rs:62-64
-        if (out_counts && !o.device_io) for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
-        return CGVEC_OK;
-    }
-    if (!queries) return fail(CGVEC_ERR_BAD_ARG, "queries is NULL");
+// The search proper (arguments validated by cgvec_search_ex): multi-device parent, or one device / one rank of a sharded index.
+static int search_ex_body(Index* ix, const float* queries, uint32_t nq, uint32_t k, const cgvec_search_opts& o, uint64_t* out_rows,
+                          uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts) {
     if (!ix->parts.empty()) return multi_search(ix, queries, nq, k, o, out_rows, out_ids, out_scores, out_counts);
     CUDA_TRY(cudaSetDevice(ix->device));
     const uint64_t n_total_hint = ix->n;                       // local rows; sharded ranks may be empty individually
@@ -681,6 +763,103 @@ CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, u
     return finish(CGVEC_OK);
 }
 
+// Group commit of concurrent batch-1 callers (SURVEY §8b "Threading"; multi_vector_search, search.rs:347-361, fans out one
+// search_similar per query with try_join_all).  Every batch-1 scan is a full pass over the matrix, so callers that arrive
+// while a pass is in flight are not given passes of their own: the first caller to find no pass in flight becomes the
+// leader, takes every queued request compatible with the oldest one (same k, metric, path) up to `coalesce_max`, serves them as ONE
+// multi-query call (<= 4 queries per exact-order launch, the tensor path for larger groups; bit-exact either way) and hands
+// the results out.  A lone caller pays one uncontended mutex; nobody waits for a batch to fill.
+struct Index::PendingSearch {
+    const float* query; uint32_t k; cgvec_search_opts o;
+    uint64_t* out_rows; uint8_t (*out_ids)[16]; float* out_scores; uint32_t* out_count;
+    int rc = CGVEC_OK; bool done = false; std::string err;
+};
+static int coalesced_search(Index* ix, const float* query, uint32_t k, const cgvec_search_opts& o, uint64_t* out_rows,
+                            uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts) {
+    Index::PendingSearch me;
+    me.query = query; me.k = k; me.o = o; me.out_rows = out_rows; me.out_ids = out_ids; me.out_scores = out_scores; me.out_count = out_counts;
+    std::unique_lock<std::mutex> lk(ix->co_mu);
+    ix->co_queue.push_back(&me);
+    while (true) {
+        ix->co_cv.wait(lk, [&] { return me.done || !ix->co_leader; });
+        if (me.done) break;
+        ix->co_leader = true;                                    // lead one batch: the oldest request and everything compatible with it
+        std::vector<Index::PendingSearch*> batch;
+        const Index::PendingSearch* head = ix->co_queue.front();
+        const uint32_t cap = (uint32_t)std::max(1, ix->opt_coalesce_max);
+        for (auto it = ix->co_queue.begin(); it != ix->co_queue.end() && batch.size() < cap;) {
+            Index::PendingSearch* r = *it;
+            if (r->k == head->k && r->o.metric == head->o.metric && r->o.path == head->o.path) { batch.push_back(r); it = ix->co_queue.erase(it); }
+            else ++it;
+        }
+        lk.unlock();
+        const uint32_t b = (uint32_t)batch.size(), kk = batch[0]->k;
+        int rc;
+        if (b == 1) {
+            Index::PendingSearch* r = batch[0];
+            rc = search_ex_body(ix, r->query, 1, kk, r->o, r->out_rows, r->out_ids, r->out_scores, r->out_count);
+            r->rc = rc; if (rc) r->err = g_err;
+        } else {
+            std::vector<float> q((size_t)b * ix->dim);
+            std::vector<uint64_t> rows((size_t)b * kk);
+            std::vector<float> scores((size_t)b * kk);
+            std::vector<uint32_t> counts(b);
+            std::vector<uint8_t> ids;
+            bool want_ids = false;
+            for (uint32_t i = 0; i < b; ++i) { memcpy(&q[(size_t)i * ix->dim], batch[i]->query, ix->dim * sizeof(float)); want_ids = want_ids || batch[i]->out_ids; }
+            if (want_ids) ids.resize((size_t)b * kk * 16);
+            rc = search_ex_body(ix, q.data(), b, kk, batch[0]->o, rows.data(), want_ids ? reinterpret_cast<uint8_t(*)[16]>(ids.data()) : nullptr,
+                                scores.data(), counts.data());
+            for (uint32_t i = 0; i < b; ++i) {
+                Index::PendingSearch* r = batch[i];
+                r->rc = rc;
+                if (rc) { r->err = g_err; continue; }
+                if (r->out_rows) memcpy(r->out_rows, &rows[(size_t)i * kk], kk * sizeof(uint64_t));
+                if (r->out_scores) memcpy(r->out_scores, &scores[(size_t)i * kk], kk * sizeof(float));
+                if (r->out_ids) memcpy(r->out_ids, &ids[(size_t)i * kk * 16], (size_t)kk * 16);
+                if (r->out_count) *r->out_count = counts[i];
+            }
+            ix->co_batches++; ix->co_queries += b;
+        }
+        lk.lock();
+        for (auto* r : batch) r->done = true;
+        ix->co_leader = false;
+        ix->co_cv.notify_all();
+        if (me.done) break;                                      // else: my request was not compatible with that batch's head; go again
+    }
+    lk.unlock();
+    if (me.rc) return fail(me.rc, "%s", me.err.c_str());
+    return CGVEC_OK;
+}
+
+CGVEC_EXPORT int cgvec_search_ex(const cgvec_index* cix, const float* queries, uint32_t nq, uint32_t k,
+                                 const cgvec_search_opts* opts, uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores,
+                                 uint32_t* out_counts) {
+    RwGuard rw_guard_(cix, false);
+    Index* ix = const_cast<cgvec_index*>(cix);
+    if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
+    cgvec_search_opts o{};
+    o.struct_size = sizeof(o);
+    if (opts) {
+        if (opts->struct_size < sizeof(uint32_t) * 4) return fail(CGVEC_ERR_BAD_ARG, "opts->struct_size is not set");
+        memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
+    }
+    if (o.metric != CGVEC_COSINE && o.metric != CGVEC_DOT && o.metric != CGVEC_L2) return fail(CGVEC_ERR_BAD_ARG, "unknown metric %d", (int)o.metric);
+    if (o.formula < CGVEC_FORMULA_SIMD || o.formula > CGVEC_FORMULA_BASELINE) return fail(CGVEC_ERR_BAD_ARG, "unknown formula %d", (int)o.formula);
+    if (o.formula != CGVEC_FORMULA_SIMD && o.metric != CGVEC_COSINE)
+        return fail(CGVEC_ERR_UNSUPPORTED, "formulas other than SIMD exist for cosine only (the reference has no scalar dot / L2)");
+    if (o.device_io && out_ids) return fail(CGVEC_ERR_BAD_ARG, "out_ids cannot be produced with device_io");
+    if (o.device_io && o.formula != CGVEC_FORMULA_SIMD) return fail(CGVEC_ERR_UNSUPPORTED, "device_io supports the SIMD formula only");
+    if (nq == 0 || k == 0) {                                   // surreal_store.rs:62-64
+        if (out_counts && !o.device_io) for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+        return CGVEC_OK;
+    }
+    if (!queries) return fail(CGVEC_ERR_BAD_ARG, "queries is NULL");
+    if (nq == 1 && ix->opt_coalesce && !o.device_io && !o.stream && o.formula == CGVEC_FORMULA_SIMD && ix->world == 1)
+        return coalesced_search(ix, queries, k, o, out_rows, out_ids, out_scores, out_counts);
+    return search_ex_body(ix, queries, nq, k, o, out_rows, out_ids, out_scores, out_counts);
+}
+
 CGVEC_EXPORT int cgvec_search(const cgvec_index* ix, const float* queries, uint32_t nq, uint32_t k, cgvec_metric metric,
                               uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts) {
     cgvec_search_opts o{};
@@ -770,6 +949,7 @@ int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int fo
 }  // namespace
 
 CGVEC_EXPORT int cgvec_row_of_id(const cgvec_index* ix, const uint8_t id[16], uint64_t* out_local_row) {
+    RwGuard rw_guard_(ix, false);
     if (!ix || !id) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     auto it = ix->id2row.find(id_key(id));
     if (it == ix->id2row.end()) return fail(CGVEC_ERR_NOT_FOUND, "id not present");
@@ -778,6 +958,7 @@ CGVEC_EXPORT int cgvec_row_of_id(const cgvec_index* ix, const uint8_t id[16], ui
 }
 
 CGVEC_EXPORT int cgvec_get_row(const cgvec_index* cix, uint64_t local_row, float* out_row) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !out_row) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     if (local_row >= ix->n) return fail(CGVEC_ERR_NOT_FOUND, "row %llu out of range", (unsigned long long)local_row);
@@ -806,6 +987,7 @@ CGVEC_EXPORT int cgvec_get_row(const cgvec_index* cix, uint64_t local_row, float
 
 // Bulk read-back of rows [first, first+n) widened to f32 (row-major n x dim): snapshot / parity checks.
 CGVEC_EXPORT int cgvec_get_rows(const cgvec_index* cix, uint64_t first, uint64_t n, float* out) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (n == 0) return CGVEC_OK;
@@ -839,6 +1021,7 @@ CGVEC_EXPORT int cgvec_get_rows(const cgvec_index* cix, uint64_t first, uint64_t
 }
 
 CGVEC_EXPORT int cgvec_get(const cgvec_index* ix, const uint8_t id[16], float* out_row) {
+    RwGuard rw_guard_(ix, false);
     uint64_t row = 0;
     int rc = cgvec_row_of_id(ix, id, &row);
     if (rc) return rc;
@@ -847,6 +1030,7 @@ CGVEC_EXPORT int cgvec_get(const cgvec_index* ix, const uint8_t id[16], float* o
 
 CGVEC_EXPORT int cgvec_rescore(const cgvec_index* cix, const float* query, const uint64_t* local_rows, uint32_t n, cgvec_metric metric,
                                cgvec_formula formula, float* out_scores) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (n == 0) return CGVEC_OK;
@@ -880,6 +1064,7 @@ CGVEC_EXPORT int cgvec_rescore(const cgvec_index* cix, const float* query, const
 }
 
 CGVEC_EXPORT int cgvec_distances_first(const cgvec_index* cix, const float* query, uint64_t limit, float* out, uint64_t* out_n) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !query) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     uint64_t m = limit < ix->n ? limit : ix->n;
@@ -919,6 +1104,7 @@ CGVEC_EXPORT int cgvec_distances_first(const cgvec_index* cix, const float* quer
 // int8 quantised scan: quantize_batch (optimization.rs:212-224,268-274) + search_optimized (:63-150)
 // ================================================================================================
 CGVEC_EXPORT int cgvec_quantize_i8(cgvec_index* ix) {
+    CGVEC_WRITE_GUARD(ix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (!ix->parts.empty() || ix->world > 1) return fail(CGVEC_ERR_UNSUPPORTED, "the int8 scan serves single-GPU indexes");
     CUDA_TRY(cudaSetDevice(ix->device));
@@ -944,6 +1130,7 @@ CGVEC_EXPORT int cgvec_quantize_i8(cgvec_index* ix) {
 }
 
 CGVEC_EXPORT int cgvec_get_codes_i8(const cgvec_index* cix, uint64_t first, uint64_t n, uint8_t* out) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || (!out && n)) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     if (first + n > ix->n_codes) return fail(CGVEC_ERR_NOT_FOUND, "codes [%llu, %llu) out of range (call cgvec_quantize_i8 first)", (unsigned long long)first, (unsigned long long)(first + n));
@@ -1040,6 +1227,7 @@ static int i8_initial_fill_end(Index* ix, uint32_t limit, uint64_t* out) {
 
 CGVEC_EXPORT int cgvec_search_i8(const cgvec_index* cix, const float* query, uint32_t limit, uint64_t* out_rows, float* out_scores,
                                  uint32_t* out_count) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !query) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     if (out_count) *out_count = 0;
@@ -1125,6 +1313,7 @@ CGVEC_EXPORT int cgvec_search_i8(const cgvec_index* cix, const float* query, uin
 //   [u64 vector_count][u64 dimension][vector_count * dimension f32, row-major], native endian, exact file size
 // ================================================================================================
 CGVEC_EXPORT int cgvec_save_flat(const cgvec_index* cix, const char* path) {
+    RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !path) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     FILE* f = fopen(path, "wb");
@@ -1146,6 +1335,7 @@ CGVEC_EXPORT int cgvec_save_flat(const cgvec_index* cix, const char* path) {
 }
 
 CGVEC_EXPORT int cgvec_load_flat(cgvec_index* ix, const char* path, uint64_t* out_rows_loaded) {
+    CGVEC_WRITE_GUARD(ix);
     if (!ix || !path) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");
     FILE* f = fopen(path, "rb");
     if (!f) return fail(CGVEC_ERR_BAD_ARG, "Failed to open mmap file: %s", path);
@@ -1267,6 +1457,7 @@ CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
         int rc = cgvec_get_stats(static_cast<const cgvec_index*>(ix->parts[0]), out);
         if (rc) return rc;
         out->rows = ix->n;
+        out->coalesced_batches = ix->co_batches.load(); out->coalesced_queries = ix->co_queries.load();
         for (size_t s = 1; s < ix->parts.size(); ++s) {
             cgvec_stats t;
             rc = cgvec_get_stats(static_cast<const cgvec_index*>(ix->parts[s]), &t);
@@ -1296,6 +1487,7 @@ CGVEC_EXPORT int cgvec_get_stats(const cgvec_index* cix, cgvec_stats* out) {
     out->exchange_mode = ix->last_exchange.load();
     out->tc_main_ms_total = ix->tc_main_ms_total;
     out->tc_main_timed = ix->tc_main_timed;
+    out->coalesced_batches = ix->co_batches.load(); out->coalesced_queries = ix->co_queries.load();
     return CGVEC_OK;
 }
 
@@ -1312,6 +1504,8 @@ CGVEC_EXPORT int cgvec_set_option(cgvec_index* ix, const char* key, int64_t valu
     else if (k == "reset_timing") { drain_timings(ix); ix->scan_ms_total = 0; ix->scan_timed = 0; ix->tc_main_ms_total = 0; ix->tc_main_timed = 0; }
     else if (k == "max_batch") ix->opt_max_nq = (int)value;
     else if (k == "pdl") ix->opt_pdl = (int)value;
+    else if (k == "coalesce") ix->opt_coalesce = (int)value;
+    else if (k == "coalesce_max") ix->opt_coalesce_max = (int)value;
     else if (k == "trace") {
         cudaSetDevice(ix->device);
         if (value && !ix->d_trace) {

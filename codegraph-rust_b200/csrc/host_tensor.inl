@@ -230,10 +230,10 @@ int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
         const uint32_t total = nq * kp;
         if (f32)
             tc_rescore_kernel<float><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
-                                                                             ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, formula, ix->row_offset, c->d_exact);
+                                                                             ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, formula, ix->row_offset, ix->blk_rows, ix->n_shards, c->d_exact);
         else
             tc_rescore_kernel<__half><<<(total * 8 + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(ix->d_rows), ix->dim, ix->ld, d_q, qstride, d_na,
-                                                                              ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, formula, ix->row_offset, c->d_exact);
+                                                                              ix->d_norms, c->d_cand, kTcCap, kp, nq, METRIC_COSINE, formula, ix->row_offset, ix->blk_rows, ix->n_shards, c->d_exact);
         ix->launches++;
         CUDA_TRY(cudaGetLastError());
     }

@@ -61,7 +61,7 @@ struct TcParams {
     uint32_t metric;            // METRIC_COSINE or METRIC_DOT
     uint32_t tmem_cols;         // power of two >= 2*N, >= 32
     uint32_t tf32;              // 0: f16 rows/queries (kind::f16, 64 elements per 128-byte K-block); 1: f32 rows/queries as TF32 (kind::tf32, 32)
-    uint32_t debug;             // bit 0: skip the MMAs, bit 1: skip the epilogue body (bandwidth triage only; results invalid)
+    uint32_t debug;             // bit 0: skip the MMAs, bit 1: skip the epilogue body, bit 2: K2b streams the query block for the first tile only (triage only; results invalid)
     uint64_t row_offset;
     uint32_t blk_rows, n_shards, shard_id;
 };
@@ -234,14 +234,15 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
     __syncwarp();
 }
 
+// `pd` is the lane's parked survivor: it lives across tiles and is flushed by the caller at the start of the NEXT tile's
+// epilogue (by then the atomic that reserved its slot has long returned) and once after the last tile.
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t taddr, const float* __restrict__ s_nthr, uint64_t row,
-                                                 bool valid, float inv, uint32_t col_begin, uint32_t col_end) {
+                                                 bool valid, float inv, uint32_t col_begin, uint32_t col_end, TcPending& pd) {
     if ((p.debug & 2u) || col_begin >= col_end) return;
-    const uint64_t b = row / p.blk_rows, rr = row - b * p.blk_rows;
-    const uint32_t grow = (uint32_t)((b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);   // global row of this lane
+    const uint32_t row32 = (uint32_t)row;                                 // shards hold < 2^32 rows: 32-bit division
+    const uint32_t b = row32 / p.blk_rows, rr = row32 - b * p.blk_rows;
+    const uint32_t grow = (uint32_t)(((uint64_t)b * p.n_shards + p.shard_id) * p.blk_rows + rr + p.row_offset);   // global row of this lane
     const uint32_t boot_slot = (uint32_t)(row - p.row_begin);
-    TcPending pd;
-    pd.q = kTcNoPending; pd.pos = 0; pd.key = 0;
     uint32_t ra[16], rb[16];
     tmem_ld_x16(taddr + col_begin, ra);
     for (uint32_t c0 = col_begin; c0 < col_end; c0 += 32) {
@@ -255,7 +256,6 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tad
             tc_epilogue_chunk(p, rb, s_nthr, c0 + 16, grow, boot_slot, valid, inv, pd);
         }
     }
-    tc_flush_pending(p, pd);
 }
 
 // Negated thresholds of this launch -> shared memory (padding columns get -inf so they can never survive).
@@ -369,9 +369,23 @@ __device__ __noinline__ void tc_selector_loop(const TcParams& p, uint64_t* s_sor
 }
 // Epilogue warps re-read their columns' thresholds from global memory once per tile (behind the accumulator wait), so a
 // threshold published by any selector takes effect everywhere within one tile time.
-__device__ __forceinline__ void tc_refresh_thresholds(const TcParams& p, float* s_nthr, uint32_t col_begin, uint32_t col_end, uint32_t lane) {
-    for (uint32_t j = col_begin + lane; j < col_end; j += 32)
-        if (j < p.nq) s_nthr[j] = -ld_volatile_f32(p.thr + j);
+// The loads are ISSUED before the warp waits for its accumulator and CONSUMED (negated into shared memory) after it has handed
+// the accumulator back, so their L2 round trip (the single most-sampled stall of the first version of this kernel) hides
+// behind the tile instead of sitting in front of it; the thresholds a tile is filtered with are one tile older.
+constexpr uint32_t kTcThrRegs = kTc2MaxN / 2 / 32;                     // columns per epilogue warp / lanes
+__device__ __forceinline__ void tc_thresholds_issue(const TcParams& p, float (&pre)[kTcThrRegs], uint32_t col_begin, uint32_t col_end, uint32_t lane) {
+#pragma unroll
+    for (uint32_t u = 0; u < kTcThrRegs; ++u) {
+        const uint32_t j = col_begin + lane + 32 * u;
+        pre[u] = (j < col_end && j < p.nq) ? ld_volatile_f32(p.thr + j) : 0.0f;
+    }
+}
+__device__ __forceinline__ void tc_thresholds_commit(const TcParams& p, const float (&pre)[kTcThrRegs], float* s_nthr, uint32_t col_begin, uint32_t col_end, uint32_t lane) {
+#pragma unroll
+    for (uint32_t u = 0; u < kTcThrRegs; ++u) {
+        const uint32_t j = col_begin + lane + 32 * u;
+        if (j < col_end && j < p.nq) s_nthr[j] = -pre[u];
+    }
     __syncwarp();
 }
 
@@ -505,23 +519,31 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t q4 = warp & 3;
         const uint32_t col_split = ((p.N / 16 + 1) / 2) * 16;
         const uint32_t col_begin = warp < 4 ? 0u : col_split, col_end = warp < 4 ? col_split : p.N;
+        TcPending pd;
+        pd.q = kTcNoPending; pd.pos = 0; pd.key = 0;
+        const bool cosine = p.metric == METRIC_COSINE;
+        auto tile_row = [&](uint64_t t) { return (first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows + q4 * 32 + lane; };   // local row
+        auto row_ok = [&](uint64_t row) { return row < p.n_rows && row < p.row_end; };
+        float nb_next = (cosine && my_tiles && row_ok(tile_row(0))) ? p.norms[tile_row(0)] : 0.0f;
         for (uint64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = t & 1;
-            const uint64_t row = (first_tile + blockIdx.x + t * gridDim.x) * kTcTileRows + q4 * 32 + lane;   // local row
-            const bool valid = row < p.n_rows && row < p.row_end;
-            float inv = 1.0f;
-            if (p.metric == METRIC_COSINE) {
-                const float nb = valid ? p.norms[row] : 0.0f;
-                inv = nb > 0.0f ? rsqrtf(nb) : 0.0f;                     // zero-norm row -> cosine 0 (simd_ops.rs:73-74)
-            }
-            if (p.sel_on) tc_refresh_thresholds(p, s_nthr, col_begin, col_end, lane);
+            const uint64_t row = tile_row(t);
+            const bool valid = row_ok(row);
+            const float nb = nb_next;
+            if (cosine && t + 1 < my_tiles) { const uint64_t rn = tile_row(t + 1); nb_next = row_ok(rn) ? p.norms[rn] : 0.0f; }   // one tile ahead
+            const float inv = cosine ? (nb > 0.0f ? rsqrtf(nb) : 0.0f) : 1.0f;    // zero-norm row -> cosine 0 (simd_ops.rs:73-74)
+            float thr_pre[kTcThrRegs];
+            if (p.sel_on) tc_thresholds_issue(p, thr_pre, col_begin, col_end, lane);
             mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
             tc_fence_after();
-            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, col_begin, col_end);
+            tc_flush_pending(p, pd);                                     // survivor parked by the previous tile
+            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, col_begin, col_end, pd);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (p.sel_on) tc_thresholds_commit(p, thr_pre, s_nthr, col_begin, col_end, lane);
         }
+        tc_flush_pending(p, pd);
         if (lane == 0) atomicAdd(s_epi_done, 1u);
     } else if (p.sel_on) {                                           // warps 6 and 7: selectors
         tc_selector_loop(p, s_sort + (size_t)(warp - 6) * p.sel_cap, s_epi_done, 2 * blockIdx.x + (warp - 6), 2 * gridDim.x, lane);
@@ -644,13 +666,14 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(&empty_bar[s], ph);
                 if (elect_one()) {
                     uint8_t* st = smem + (size_t)s * lay.stage_bytes;
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * lay.stage_bytes);     // both CTAs' bytes land on the leader
+                    const bool skip_b = (p.debug & 4u) && t > 0;                  // triage: the query block is not re-streamed (results invalid)
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], skip_b ? 2 * lay.a_bytes : 2 * lay.stage_bytes);   // both CTAs' bytes land on the leader
                     if (p.box4d) {
                         tma_load_4d_2sm(st, &tmA, (int)(g * p.kbs), row0 >> 3, &full_bar[s], pol);
-                        tma_load_4d_2sm(st + lay.a_bytes, &tmB, (int)(g * p.kbs), (int)((rank * half_n) >> 3), &full_bar[s], pol_keep);
+                        if (!skip_b) tma_load_4d_2sm(st + lay.a_bytes, &tmB, (int)(g * p.kbs), (int)((rank * half_n) >> 3), &full_bar[s], pol_keep);
                     } else {
                         tma_load_2d_2sm(st, &tmA, (int)g * kbe, row0, &full_bar[s], pol);
-                        tma_load_2d_2sm(st + lay.a_bytes, &tmB, (int)g * kbe, (int)(rank * half_n), &full_bar[s], pol_keep);
+                        if (!skip_b) tma_load_2d_2sm(st + lay.a_bytes, &tmB, (int)g * kbe, (int)(rank * half_n), &full_bar[s], pol_keep);
                     }
                 }
                 __syncwarp();
@@ -668,26 +691,34 @@ tc2_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t q4 = warp & 3;
         const uint32_t col_split = ((p.N / 16 + 1) / 2) * 16;
         const uint32_t col_begin = warp < 4 ? 0u : col_split, col_end = warp < 4 ? col_split : p.N;
+        TcPending pd;
+        pd.q = kTcNoPending; pd.pos = 0; pd.key = 0;
+        const bool cosine = p.metric == METRIC_COSINE;
+        auto tile_row = [&](uint64_t t) { return (first_tile + pair + t * npairs) * kPairRows + rank * kTcTileRows + q4 * 32 + lane; };
+        auto row_ok = [&](uint64_t row) { return row < p.n_rows && row < p.row_end; };
+        float nb_next = (cosine && my_tiles && row_ok(tile_row(0))) ? p.norms[tile_row(0)] : 0.0f;
         for (uint64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = t & 1;
-            const uint64_t row = (first_tile + pair + t * npairs) * kPairRows + rank * kTcTileRows + q4 * 32 + lane;
-            const bool valid = row < p.n_rows && row < p.row_end;
-            float inv = 1.0f;
-            if (p.metric == METRIC_COSINE) {
-                const float nb = valid ? p.norms[row] : 0.0f;
-                inv = nb > 0.0f ? rsqrtf(nb) : 0.0f;
-            }
-            if (p.sel_on) tc_refresh_thresholds(p, s_nthr, col_begin, col_end, lane);
+            const uint64_t row = tile_row(t);
+            const bool valid = row_ok(row);
+            const float nb = nb_next;
+            if (cosine && t + 1 < my_tiles) { const uint64_t rn = tile_row(t + 1); nb_next = row_ok(rn) ? p.norms[rn] : 0.0f; }   // one tile ahead
+            const float inv = cosine ? (nb > 0.0f ? rsqrtf(nb) : 0.0f) : 1.0f;
+            float thr_pre[kTcThrRegs];
+            if (p.sel_on) tc_thresholds_issue(p, thr_pre, col_begin, col_end, lane);
             mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
             tc_fence_after();
-            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, col_begin, col_end);
+            tc_flush_pending(p, pd);                                     // survivor parked by the previous tile
+            tc_epilogue_tile(p, tmem_base + buf * p.N + ((q4 * 32u) << 16), s_nthr, row, valid, inv, col_begin, col_end, pd);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (leader) mbar_arrive(&tempty_bar[buf]);
                 else mbar_arrive_cta(&tempty_bar[buf], 0);
             }
+            if (p.sel_on) tc_thresholds_commit(p, thr_pre, s_nthr, col_begin, col_end, lane);
         }
+        tc_flush_pending(p, pd);
         if (lane == 0) atomicAdd(s_epi_done, 1u);
     } else if (p.sel_on) {                                           // warps 6 and 7: selectors
         tc_selector_loop(p, s_sort + (size_t)(warp - 6) * p.sel_cap, s_epi_done, 2 * blockIdx.x + (warp - 6), 2 * gridDim.x, lane);
@@ -790,7 +821,7 @@ template <typename T>
 __global__ void tc_rescore_kernel(const T* __restrict__ rows, uint32_t d, uint32_t ld, const float* __restrict__ q, uint32_t qstride,
                                   const float* __restrict__ na, const float* __restrict__ norms, const uint64_t* __restrict__ keys_in,
                                   uint32_t cap, uint32_t kp, uint32_t nq, int metric, int formula, uint64_t row_offset,
-                                  uint64_t* __restrict__ keys_out) {
+                                  uint32_t blk_rows, uint32_t n_shards, uint64_t* __restrict__ keys_out) {
     const uint32_t octet = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int L = threadIdx.x & 7;
     const uint32_t total = nq * kp;
@@ -799,7 +830,10 @@ __global__ void tc_rescore_kernel(const T* __restrict__ rows, uint32_t d, uint32
     const uint64_t key = keys_in[(size_t)qi * cap + ci];
     const bool present = key != 0ull;
     const uint32_t grow = key_row(key);
-    const uint64_t lrow = present ? (uint64_t)grow - row_offset : 0;
+    // inverse of scan_global_row: contiguous shards (n_shards == 1) are global - offset, block-dealt shards drop the other
+    // shards' blocks
+    const uint64_t gl = present ? (uint64_t)grow - row_offset : 0;
+    const uint64_t lrow = (gl / blk_rows / n_shards) * blk_rows + gl % blk_rows;
     const T* row = rows + lrow * ld;
     const float* qv = q + (size_t)qi * qstride;
     float res = 0.0f;

@@ -60,6 +60,7 @@ CGVEC_EXPORT int cgvec_stream_open(cgvec_index* ix, uint32_t max_batch, uint32_t
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_rows), on * sizeof(uint64_t)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_scores), on * sizeof(float)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_counts), max_batch * sizeof(uint32_t)));
+    ix->open_streams++;                                        // the write side refuses to run until the session is closed
     *out = s.release();
     return CGVEC_OK;
 }
@@ -128,6 +129,7 @@ CGVEC_EXPORT int cgvec_stream_flush(cgvec_stream* s, uint64_t* out_rows, float* 
 }
 
 CGVEC_EXPORT int cgvec_stream_close(cgvec_stream* s) {
+    if (s && s->ix) s->ix->open_streams--;
     stream_free(s);
     return CGVEC_OK;
 }

@@ -88,6 +88,15 @@ public:
     B200VectorStore(uint32_t dimension, const std::vector<int>& devices, cgvec_dtype storage = CGVEC_F32) : dim_(dimension) {
         check(cgvec_create(dimension, storage, devices.data(), (int)devices.size(), &idx_));
     }
+    // Deployment switch: `enable_gpu` is PerformanceConfig.enable_gpu (config_manager.rs:362-364); CODEGRAPH_ENABLE_GPU overrides
+    // it, CODEGRAPH_B200_DEVICES ("all" | count | "0,2,5") picks the GPUs.  nullptr = switched off: keep the CPU vector store.
+    static std::shared_ptr<B200VectorStore> from_env(uint32_t dimension, bool enable_gpu, cgvec_dtype storage = CGVEC_F32) {
+        cgvec_index* idx = nullptr;
+        const int rc = cgvec_create_from_env(dimension, storage, enable_gpu ? 1 : 0, &idx);
+        if (rc == CGVEC_ERR_DISABLED) return nullptr;
+        check(rc);
+        return std::shared_ptr<B200VectorStore>(new B200VectorStore(dimension, idx));
+    }
     ~B200VectorStore() override { cgvec_destroy(idx_); }
     B200VectorStore(const B200VectorStore&) = delete;
     B200VectorStore& operator=(const B200VectorStore&) = delete;
@@ -141,6 +150,7 @@ public:
     size_t len() const { return cgvec_len(idx_); }
 
 private:
+    B200VectorStore(uint32_t dimension, cgvec_index* adopted) : idx_(adopted), dim_(dimension) {}
     cgvec_index* idx_ = nullptr;
     uint32_t dim_;
 };

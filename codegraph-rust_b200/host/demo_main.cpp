@@ -24,8 +24,12 @@ static std::vector<float> hash_text_embedding(const std::string& text, size_t di
 
 int main(int argc, char** argv) {
     const size_t n = argc > 1 ? std::stoul(argv[1]) : 2000, dim = argc > 2 ? std::stoul(argv[2]) : 384, limit = argc > 3 ? std::stoul(argv[3]) : 7;
+    const int n_devices = argc > 4 ? std::stoi(argv[4]) : 1;            // > 1: the single-process multi-device store
     try {
-        auto store = std::make_shared<cgvec::B200VectorStore>((uint32_t)dim);
+        std::vector<int> devices;
+        for (int i = 0; i < n_devices; ++i) devices.push_back(i);
+        auto store = n_devices > 1 ? std::make_shared<cgvec::B200VectorStore>((uint32_t)dim, devices)
+                                   : std::make_shared<cgvec::B200VectorStore>((uint32_t)dim);
         std::vector<cgvec::CodeNode> nodes;
         for (size_t i = 0; i < n; ++i) nodes.push_back({cgvec::NodeId::from_u64(i + 1), hash_text_embedding("fn item_" + std::to_string(i) + "() {}", dim)});
         nodes.push_back({cgvec::NodeId::from_u64(999999), std::nullopt});          // skipped

@@ -16,6 +16,7 @@ pub const CGVEC_FORMULA_SIMD: c_int = 0;
 pub const CGVEC_FORMULA_SEQ: c_int = 2;
 pub const CGVEC_OK: c_int = 0;
 pub const CGVEC_ERR_NOT_FOUND: c_int = -6;
+pub const CGVEC_ERR_DISABLED: c_int = -9;
 
 #[repr(C)]
 pub struct cgvec_search_opts {
@@ -29,6 +30,7 @@ pub struct cgvec_search_opts {
 
 extern "C" {
     pub fn cgvec_create(dim: u32, storage: c_int, device_ids: *const c_int, n_devices: c_int, out: *mut *mut cgvec_index) -> c_int;
+    pub fn cgvec_create_from_env(dim: u32, storage: c_int, enable_gpu: c_int, out: *mut *mut cgvec_index) -> c_int;
     pub fn cgvec_destroy(idx: *mut cgvec_index) -> c_int;
     pub fn cgvec_reserve(idx: *mut cgvec_index, n_rows: u64) -> c_int;
     pub fn cgvec_add(idx: *mut cgvec_index, ids: *const [u8; 16], rows_f32: *const f32, n: u64) -> c_int;

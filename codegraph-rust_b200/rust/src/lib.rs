@@ -45,6 +45,17 @@ impl B200VectorStore {
         Ok(Self { h: Arc::new(Handle(raw)), dim: dimension })
     }
 
+    /// Deployment switch: `enable_gpu` is `PerformanceConfig::enable_gpu` (config_manager.rs:362-364); `CODEGRAPH_ENABLE_GPU`
+    /// overrides it and `CODEGRAPH_B200_DEVICES` ("all" | count | "0,2,5") picks the GPUs.  `Ok(None)` = switched off: keep
+    /// the CPU vector store.
+    pub fn from_env(dimension: usize, enable_gpu: bool) -> Result<Option<Self>> {
+        let mut raw = std::ptr::null_mut();
+        let rc = unsafe { ffi::cgvec_create_from_env(dimension as u32, ffi::CGVEC_F32, enable_gpu as i32, &mut raw) };
+        if rc == ffi::CGVEC_ERR_DISABLED { return Ok(None); }
+        check(rc)?;
+        Ok(Some(Self { h: Arc::new(Handle(raw)), dim: dimension }))
+    }
+
     /// One process driving several GPUs (`cgvec_create` with n_devices > 1): rows are dealt to the devices in blocks and
     /// every search merges the per-device results over NVLink.
     pub fn with_devices(dimension: usize, devices: &[i32]) -> Result<Self> {
@@ -136,12 +147,12 @@ impl VectorStore for B200VectorStore {
 
 /// Drops in where `SurrealStorageBackend` sits (surreal_store.rs:45-53): `SurrealVectorStore::new(Arc::new(B200Backend::new(store)), ef)`.
 pub struct B200Backend {
-    store: tokio::sync::RwLock<B200VectorStore>,
+    store: Arc<tokio::sync::RwLock<B200VectorStore>>,
 }
 
 impl B200Backend {
     pub fn new(store: B200VectorStore) -> Self {
-        Self { store: tokio::sync::RwLock::new(store) }
+        Self { store: Arc::new(tokio::sync::RwLock::new(store)) }
     }
 }
 
@@ -155,7 +166,10 @@ impl SurrealVectorBackend for B200Backend {
     /// distance) ascending.  `column` selects nothing (one index per dimension); `ef_search` is meaningless for an
     /// exact scan.
     async fn vector_knn(&self, _column: &str, query_embedding: Vec<f32>, limit: usize, _ef_search: usize) -> Result<Vec<(String, f32)>> {
-        let store = self.store.read().await.clone();
+        // The read guard travels into the blocking task and is held for the whole FFI search, so an upsert (write guard)
+        // can never reallocate the device matrix under a running scan.  (The C library also serialises its write side against
+        // in-flight reads with its own reader-writer lock; this keeps the shim correct on its own.)
+        let store = self.store.clone().read_owned().await;
         tokio::task::spawn_blocking(move || {
             store.knn(query_embedding, limit).map(|(ids, scores)| {
                 ids.into_iter().zip(scores).map(|(id, s)| (format!("nodes:{}", id), 1.0 - s)).collect()

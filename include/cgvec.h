@@ -69,7 +69,8 @@ typedef enum {
     CGVEC_ERR_NCCL = -5,
     CGVEC_ERR_NOT_FOUND = -6,    /* get_embedding -> None */
     CGVEC_ERR_NO_DEVICE = -7,    /* no sm_100 GPU: the product has no CPU fallback */
-    CGVEC_ERR_UNSUPPORTED = -8
+    CGVEC_ERR_UNSUPPORTED = -8,
+    CGVEC_ERR_DISABLED = -9      /* cgvec_create_from_env: performance.enable_gpu is false (config_manager.rs:362-364); keep the CPU store */
 } cgvec_status;
 
 /* Which scan kernel family serves a search. AUTO picks EXACT for small batches and TENSOR for large ones. */
@@ -87,9 +88,17 @@ typedef struct {
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 
-/* Single-process index over n_devices GPUs (row blocks dealt round-robin to the devices, merged
- * with one NCCL all-gather).  device_ids == NULL -> devices 0..n_devices-1. */
+/* Single-process index over n_devices GPUs: row blocks are dealt round-robin to the devices; a search scans on every
+ * device at once and merges over NVLink peer memory (fused exchange kernel for k <= 128 and <= 4 queries per step, peer
+ * copies into the first device + one merge launch for larger k and tensor-core batches; no NCCL in this mode).
+ * Serves every path (exact, tensor), host and device I/O (buffers on the first device), k <= 1024.
+ * device_ids == NULL -> devices 0..n_devices-1. */
 int cgvec_create(uint32_t dim, cgvec_dtype storage, const int* device_ids, int n_devices, cgvec_index** out);
+/* Deployment switch.  `enable_gpu` is the host's PerformanceConfig.enable_gpu (codegraph-core/src/config_manager.rs:362-364,
+ * default false); the environment overrides it: CODEGRAPH_ENABLE_GPU = 1/true/0/false.  Disabled -> CGVEC_ERR_DISABLED (the host
+ * keeps its CPU vector store).  CODEGRAPH_B200_DEVICES = "all" | a device COUNT ("4" -> 0..3) | a list ("0,2,5"); unset -> device 0.
+ * More than one device gives the single-process multi-device index. */
+int cgvec_create_from_env(uint32_t dim, cgvec_dtype storage, int enable_gpu, cgvec_index** out);
 
 /* One rank of a multi-process row-sharded index (one process per GPU, e.g. under torchrun).
  * All ranks must pass the same 128-byte id from cgvec_nccl_unique_id() (rank 0 creates it and
@@ -213,6 +222,8 @@ typedef struct {
     uint32_t reserved0;
     double tc_main_ms_total;     /* sum / count of device times of the tensor scan's main-range kernel ("timing" on) */
     uint64_t tc_main_timed;
+    uint64_t coalesced_batches;  /* multi-query launches formed from concurrent batch-1 cgvec_search calls (group commit) */
+    uint64_t coalesced_queries;  /* callers served through them                                                          */
 } cgvec_stats;
 int cgvec_get_stats(const cgvec_index* idx, cgvec_stats* out);
 int cgvec_set_option(cgvec_index* idx, const char* key, int64_t value);   /* tuning knobs, see DESIGN.md */

@@ -191,3 +191,34 @@ def test_merge_topk_host_contract_with_ties_nan_and_short_lists(cg):
         got_rows, got_scores = cg.merge_topk_host(rows, scores, counts, k, ascending=asc)
         assert got_rows.tolist() == [int(pool_rows[i]) for i in want], (trial, asc)
         assert np.array_equal(got_scores, np.float32([pool_scores[i] for i in want]), equal_nan=True)
+
+
+def test_enable_gpu_switch_and_device_list(cg, monkeypatch):
+    """cgvec_create_from_env: PerformanceConfig.enable_gpu (config_manager.rs:362-364, default false :419) with the CODEGRAPH_ENABLE_GPU
+    override, and CODEGRAPH_B200_DEVICES parsing.  Off -> ERR_DISABLED (host keeps its CPU store); malformed lists never abort."""
+    monkeypatch.delenv("CODEGRAPH_ENABLE_GPU", raising=False)
+    monkeypatch.delenv("CODEGRAPH_B200_DEVICES", raising=False)
+    with pytest.raises(cg.CgvecError) as e:
+        cg.Index.from_env(64, enable_gpu=False)
+    assert e.value.code == cg.ERR_DISABLED
+    monkeypatch.setenv("CODEGRAPH_ENABLE_GPU", "false")
+    with pytest.raises(cg.CgvecError) as e:
+        cg.Index.from_env(64, enable_gpu=True)                 # the environment wins over the config field
+    assert e.value.code == cg.ERR_DISABLED
+    monkeypatch.setenv("CODEGRAPH_ENABLE_GPU", "1")
+    for bad in ("0,x", "1,,2", "-1", "0", "99999"):
+        monkeypatch.setenv("CODEGRAPH_B200_DEVICES", bad)
+        with pytest.raises(cg.CgvecError) as e:
+            cg.Index.from_env(64)
+        assert e.value.code in (cg.ERR_BAD_ARG, cg.ERR_NO_DEVICE, cg.ERR_UNSUPPORTED), bad
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        for ok in ("0,1", "2", "all"):
+            monkeypatch.setenv("CODEGRAPH_B200_DEVICES", ok)
+            with pytest.raises(cg.CgvecError) as e:
+                cg.Index.from_env(64)
+            assert e.value.code == cg.ERR_NO_DEVICE

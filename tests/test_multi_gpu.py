@@ -104,14 +104,103 @@ def test_single_process_multi_device_index(cg, oracle, dtype_name):
     assert ix.distances_first(qs[2], 1500).tobytes() == oracle.compute_distances_cpu(qs[2], ref.reshape(-1), d, 1500).tobytes()
     ix.add(-rows[9:10], [ids[9]])                              # upsert by id
     assert len(ix) == n and ix.search(qs[0], 1)[0][0, 0] == 7_000
+    # k beyond the fused peer exchange (128): per-device lists pulled into the first device and merged there.  SemanticSearch
+    # over-fetches max(3*limit, limit+10) (search.rs:113), so limit 100 needs k = 300
+    for kk in (129, 300, 1024):
+        r, s, c = ix.search(qs, kk)
+        for qi in range(len(qs)):
+            wi, ws = oracle.parallel_top_k_search(qs[qi], np.vstack([ref[:9], -ref[9:10], ref[10:]]), kk)
+            assert r[qi].tolist() == wi.tolist(), (kk, qi)
+            assert s[qi].tobytes() == ws.tobytes(), (kk, qi)
     with pytest.raises(cg.CgvecError):
-        ix.search(qs, 500)                                     # beyond the peer-exchange k limit
+        ix.search(qs, 1025)                                    # beyond the fused top-k limit
     ix.close()
     # device-generated synthetic rows are the same matrix whatever the sharding
     a = cg.Index(d, dt, devices=list(range(G))); a.fill_synthetic(5000, 77, True)
     b = cg.Index(d, dt); b.fill_synthetic(5000, 77, True)
     assert a.get_rows(0, 5000).tobytes() == b.get_rows(0, 5000).tobytes()
     a.close(); b.close()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("dtype_name,k", [("f16", 100), ("f16", 300), ("f32", 10)])
+def test_single_process_multi_device_tensor_and_device_io(cg, oracle, dtype_name, k):
+    """The single-process multi-device index on the tensor-core path (batch-64, block-dealt shards: candidate rows are mapped
+    back to shard-local rows for the exact rescore) and with device-resident queries/results on the first device."""
+    import torch
+    G = min(_ngpus(), 4)
+    dt = cg.F32 if dtype_name == "f32" else cg.F16
+    rng = np.random.default_rng(59)
+    n, d, nq = 40_000 * G + 333, 256, 64
+    rows = (rng.standard_normal((n, d)) / 16).astype(np.float32)
+    qs = rng.standard_normal((nq, d)).astype(np.float32)
+    ref = rows if dt == cg.F32 else rows.astype(np.float16).astype(np.float32)
+    ix = cg.Index(d, dt, devices=list(range(G)))
+    ix.add(rows)
+    want = {qi: oracle.parallel_top_k_search(qs[qi], ref, k) for qi in range(0, nq, 9)}
+    if k <= 512:
+        r, s, c = ix.search(qs, k, cg.COSINE, path=cg.PATH_TENSOR)
+        for qi, (wi, ws) in want.items():
+            assert r[qi].tolist() == wi.tolist(), qi
+            assert s[qi].tobytes() == ws.tobytes(), qi
+        r2, s2, _ = ix.search(qs, k, cg.COSINE)                    # AUTO picks the tensor path on shards this size
+        assert r2.tobytes() == r.tobytes() and s2.tobytes() == s.tobytes()
+    # device I/O: queries and results live on the first device, the call is asynchronous on the caller's stream
+    torch.cuda.set_device(0)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        dq = torch.from_numpy(qs).cuda(non_blocking=False)
+        d_rows = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        d_scores = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        d_counts = torch.empty((nq,), dtype=torch.int32, device="cuda")
+        for path in (cg.PATH_EXACT, cg.PATH_AUTO):
+            d_rows.fill_(-1)
+            ix.search_device(dq.data_ptr(), nq, k, d_rows.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), cg.COSINE,
+                             stream=st.cuda_stream, path=path)
+            st.synchronize()
+            gr, gs = d_rows.cpu().numpy(), d_scores.cpu().numpy()
+            assert d_counts.cpu().tolist() == [k] * nq
+            for qi, (wi, ws) in want.items():
+                assert gr[qi].tolist() == wi.tolist(), (path, qi)
+                assert gs[qi].tobytes() == ws.tobytes(), (path, qi)
+    ix.close()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_non_simd_formulas_on_a_multi_device_index(cg, oracle):
+    """search_baseline (optimization.rs:376-402) and InMemoryVectorStore::search_similar (graph_vector.rs:479-494) on the
+    reference's own N=1000, d=128, seed 11223 vectors, served by a single-process multi-device index."""
+    vecs = oracle.generate_optimization_vectors(5000, 128, 11223)
+    ix = cg.Index(128, devices=list(range(min(_ngpus(), 4))))
+    ix.add(vecs)
+    for qi in (0, 1234, 4999):
+        want_i, want_d = oracle.search_baseline(vecs[qi], vecs, 10)
+        r, s, c = ix.search(vecs[qi], 10, cg.COSINE, formula=cg.FORMULA_BASELINE)
+        assert int(c[0]) == 10 and r[0].tolist() == want_i.tolist() and s[0].tobytes() == want_d.tobytes()
+        wi, ws = oracle.inmemory_search_similar(vecs[qi], vecs, 150)
+        r2, s2, _ = ix.search(vecs[qi], 150, cg.COSINE, formula=cg.FORMULA_SEQ)
+        assert r2[0].tolist() == wi.tolist() and s2[0].tobytes() == ws.tobytes()
+    ix.close()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_cpp_semantic_search_on_a_two_device_store(cg, oracle):
+    """The compiled C++ SemanticSearch mirror over a 2-device B200VectorStore with limit 100 (over-fetch 300 > the fused
+    exchange's k limit): the Rust-server deployment INTEGRATION.md recommends."""
+    import subprocess
+    demo = cg._build.build_host_demo()
+    n, dim, limit = 3000, 384, 100
+    out = subprocess.run([demo, str(n), str(dim), str(limit), "2"], capture_output=True, text=True, check=True).stdout
+    lines = dict(l.split(" ", 1) for l in out.strip().splitlines())
+    assert "error" not in lines, lines.get("error")
+    embs = np.stack([oracle.hash_text_embedding(f"fn item_{i}() {{}}", dim) for i in range(n)])
+    q = oracle.hash_text_embedding("fn item_42() { }", dim)
+    wi, ws = oracle.parallel_top_k_search(q, embs, limit)
+    assert lines["search_similar"].split() == [f"00000000-0000-0000-0000-{int(i) + 1:012x}" for i in wi]
+    si, snorm, _ = oracle.search_by_embedding(q, embs, limit)
+    sem = [t.rsplit(":", 1) for t in lines["semantic"].split()]
+    assert [u for u, _ in sem] == [f"00000000-0000-0000-0000-{int(i) + 1:012x}" for i in si]
+    assert np.float32([float.fromhex(x) for _, x in sem]).tobytes() == snorm.tobytes()
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")

@@ -286,6 +286,57 @@ def test_concurrent_searches_are_reentrant(cg, oracle):
     ix.close()
 
 
+def test_concurrent_batch1_callers_are_coalesced(cg, oracle):
+    """Group commit (SURVEY §8b Threading; multi_vector_search, search.rs:347-361): 16 threads issuing batch-1 searches against
+    one index are served by shared multi-query passes — every caller still gets exactly the oracle's answer (rows, score bytes,
+    ids), mixed k / metric requests are never merged, and the pass count drops below one per caller."""
+    import threading, uuid
+    rng = np.random.default_rng(116)
+    n, d = 300_000, 128
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    ids = [uuid.UUID(int=i + 1) for i in range(2000)]
+    qs = rng.standard_normal((16, d)).astype(np.float32)
+    ix = cg.Index(d)
+    ix.add(rows[:2000], ids); ix.add(rows[2000:])
+    ks = [10, 10, 10, 25]                                       # thread i uses k = ks[i % 4]; thread 7 uses L2
+    want = []
+    for i in range(16):
+        metric = oracle.L2 if i == 7 else oracle.COSINE
+        want.append(oracle.parallel_top_k_search(qs[i], rows, ks[i % 4], metric=metric))
+    reps = 12
+    got = [[None] * reps for _ in range(16)]
+    start = threading.Barrier(16)
+
+    def work(i):
+        start.wait()
+        for r in range(reps):
+            got[i][r] = ix.search(qs[i], ks[i % 4], cg.L2 if i == 7 else cg.COSINE, want_ids=True)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(16)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for i in range(16):
+        wi, ws = want[i]
+        for r in range(reps):
+            gr, gs, gc, gids = got[i][r]
+            assert gr[0].tolist() == wi.tolist(), (i, r)
+            assert gs[0].tobytes() == ws.tobytes(), (i, r)
+            assert int(gc[0]) == len(wi)
+            for j, row in enumerate(wi):
+                want_id = ids[int(row)].bytes if int(row) < 2000 else bytes(16)
+                assert gids[0, j].tobytes() == want_id
+    st = ix.stats()
+    assert st.coalesced_batches > 0 and st.coalesced_queries >= 2 * st.coalesced_batches
+    # switched off: every caller scans on its own again, same answers
+    ix.set_option("coalesce", 0)
+    b0 = ix.stats().coalesced_batches
+    th = [threading.Thread(target=work, args=(i,)) for i in range(16)]
+    start.reset()
+    [t.start() for t in th]; [t.join() for t in th]
+    assert ix.stats().coalesced_batches == b0
+    for i in range(16):
+        assert got[i][-1][0][0].tolist() == want[i][0].tolist()
+    ix.close()
+
+
 def test_config2_full_size_1m_x_768(cg, oracle):
     """BASELINE config 2 at full size: 1M x 768 f32, batch-1, top-10, checked against the oracle on the rows
     read back from HBM; plus size-independent properties (planted neighbour, self-match, idempotence)."""

@@ -19,6 +19,9 @@ def main():
     ap.add_argument("--opt", action="append", default=[])
     args = ap.parse_args()
     cg = ge.load_package()
+    if os.environ.get("CGVEC_AB_LIB"):                      # A/B runs: load another build of the library (tools/r02/gpu_k.sh)
+        cg._build.LIB = os.environ["CGVEC_AB_LIB"]
+        cg.load_library(build=False)
     import torch
     ix = cg.Index(args.dim, cg.F16 if args.dtype == "f16" else cg.F32)
     ix.reserve(args.rows)
