@@ -20,6 +20,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/cgvec.h"
 #include "aux_kernels.cuh"
 #include "common.cuh"
@@ -167,7 +169,7 @@ struct Index {
     std::vector<uint32_t> trace_kinds;      // 1 = scan, 2 = merge, 3 = exchange
     static constexpr uint32_t kTraceCap = 16384;
     int opt_tc_target = 0, opt_tc_l2promo = 2, opt_tc_prefetch = 0, opt_tc_first = 0, opt_tc_kernel = 0, opt_tc_debug = 0, opt_tc2_max_n = kTc2MaxN;
-    int opt_tc_min_nq = 8, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0, opt_tc_kbs = 0, opt_tc_flow = 0;
+    int opt_tc_min_nq = 0, opt_tc_stages = 0, opt_tc_max_n = kTcMaxN, opt_tc_margin = 0, opt_tc_kbs = 0, opt_tc_flow = 0;
     std::atomic<uint64_t> tc_batches{0}, tc_fallbacks{0};
 
     // stats
@@ -221,6 +223,15 @@ using RwGuard = RwGuardT<Index>;
 #define CGVEC_WRITE_GUARD(ix)                                                                                              \
     RwGuard rw_guard_(ix, true);                                                                                           \
     if ((ix) && (ix)->open_streams.load() > 0) return fail(CGVEC_ERR_UNSUPPORTED, "close the index's cgvec_stream sessions before writing to it")
+
+// NVTX range around a host-side phase (SURVEY §5 aux: tracing).  Header-only NVTX3: a no-op costing one predicted branch unless
+// a tool (nsys, ncu --nvtx) injected itself into the process.  Names: cgvec.<phase>.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 int check_device(int device) {
     int count = 0;
@@ -534,6 +545,7 @@ CGVEC_EXPORT int cgvec_reserve(cgvec_index* ix, uint64_t n_rows) {
 }
 
 static int add_impl(cgvec_index* ix, const uint8_t (*ids)[16], const void* rows, uint64_t n, uint32_t src_esize) {
+    NvtxRange nvtx_("cgvec.add");
     CGVEC_WRITE_GUARD(ix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
     if (n == 0) return CGVEC_OK;
@@ -662,6 +674,7 @@ CGVEC_EXPORT uint32_t cgvec_dim(const cgvec_index* ix) { return ix ? ix->dim : 0
 // The search proper (arguments validated by cgvec_search_ex): multi-device parent, or one device / one rank of a sharded index.
 static int search_ex_body(Index* ix, const float* queries, uint32_t nq, uint32_t k, const cgvec_search_opts& o, uint64_t* out_rows,
                           uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts) {
+    NvtxRange nvtx_("cgvec.search");
     if (!ix->parts.empty()) return multi_search(ix, queries, nq, k, o, out_rows, out_ids, out_scores, out_counts);
     CUDA_TRY(cudaSetDevice(ix->device));
     const uint64_t n_total_hint = ix->n;                       // local rows; sharded ranks may be empty individually
@@ -794,6 +807,7 @@ static int coalesced_search(Index* ix, const float* query, uint32_t k, const cgv
         }
         lk.unlock();
         const uint32_t b = (uint32_t)batch.size(), kk = batch[0]->k;
+        NvtxRange nvtx_(b > 1 ? "cgvec.coalesced_batch" : "cgvec.single_caller");
         int rc;
         if (b == 1) {
             Index::PendingSearch* r = batch[0];
@@ -884,6 +898,7 @@ static void launch_rescore_t(Index* ix, const float* d_q, const uint64_t* d_loca
 namespace {
 int search_formula(Index* ix, SearchCtx* c, const float* d_q, uint32_t k, int formula, cudaStream_t st, uint64_t* h_rows,
                    float* h_scores, uint32_t* h_count) {
+    NvtxRange nvtx_("cgvec.search_formula");
     const int ascending = (formula == CGVEC_FORMULA_BASELINE);
     const uint64_t n = ix->n;
     const uint32_t want = (uint32_t)(k < n ? k : n);
@@ -1030,6 +1045,7 @@ CGVEC_EXPORT int cgvec_get(const cgvec_index* ix, const uint8_t id[16], float* o
 
 CGVEC_EXPORT int cgvec_rescore(const cgvec_index* cix, const float* query, const uint64_t* local_rows, uint32_t n, cgvec_metric metric,
                                cgvec_formula formula, float* out_scores) {
+    NvtxRange nvtx_("cgvec.rescore");
     RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix) return fail(CGVEC_ERR_BAD_ARG, "index is NULL");
@@ -1227,6 +1243,7 @@ static int i8_initial_fill_end(Index* ix, uint32_t limit, uint64_t* out) {
 
 CGVEC_EXPORT int cgvec_search_i8(const cgvec_index* cix, const float* query, uint32_t limit, uint64_t* out_rows, float* out_scores,
                                  uint32_t* out_count) {
+    NvtxRange nvtx_("cgvec.search_i8");
     RwGuard rw_guard_(cix, false);
     Index* ix = const_cast<cgvec_index*>(cix);
     if (!ix || !query) return fail(CGVEC_ERR_BAD_ARG, "NULL argument");

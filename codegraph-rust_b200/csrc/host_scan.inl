@@ -102,6 +102,7 @@ int launch_scan_m(int metric, uint32_t nq, const ScanParams& p, const ScanGeom& 
 int merge_lists(Index* ix, SearchCtx* c, const uint64_t* in, uint32_t nq, uint32_t lists, uint32_t k, int ascending,
                 uint64_t* final_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, cudaStream_t st,
                 size_t q_stride, size_t l_stride, uint32_t list_len = 0, int sorted_in = 1) {
+    NvtxRange nvtx_("cgvec.merge");
     if (list_len == 0) list_len = k;
     {
         int arc = ensure_smem_attr(merge_topk_kernel, kMergeMaxKeys * 8);
@@ -154,6 +155,7 @@ int ensure_parts(SearchCtx* c, size_t need_part);
 // the `world` lists and decodes.  The single collective of the path.
 int exchange_and_decode(Index* ix, SearchCtx* c, uint64_t* local_keys, uint32_t nq, uint32_t k, int ascending, cudaStream_t st,
                         uint64_t* d_rows, float* d_scores, uint32_t* d_counts) {
+    NvtxRange nvtx_("cgvec.exchange.nccl");
     size_t per_rank = (size_t)nq * k;
     {   // the gathered [rank][query][k] layout is re-packed to [query][rank][k] in the merge scratch
         int rc = ensure_parts(c, per_rank * (size_t)ix->world);
@@ -193,6 +195,7 @@ int ensure_parts(SearchCtx* c, size_t need_part) {
 int local_exact(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t k, int metric, cudaStream_t st,
                 uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts,
                 const uint64_t** partials_out = nullptr, uint32_t* lists_out = nullptr) {
+    NvtxRange nvtx_("cgvec.exact_scan");
     ScanGeom g;
     int rc = plan_scan(ix, k, nq, &g);
     if (rc) return rc;
@@ -250,6 +253,7 @@ int scan_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t nq, uint32_t 
         int rc = local_exact(ix, c, d_q, nq, k, metric, st, nullptr, nullptr, nullptr, nullptr, &partials, &lists);
         if (rc) return rc;
         if (lists <= 256) {
+            NvtxRange nvtx_x("cgvec.exchange.p2p");
             std::lock_guard<std::mutex> lk(ix->comm_mu);          // same step order on every rank
             XchgParams xp{};
             xp.partials = partials; xp.n_lists = lists; xp.k = k; xp.nq = nq; xp.ascending = (metric == CGVEC_L2);

@@ -105,6 +105,7 @@ uint32_t tc_batch_limit(const Index* ix, uint32_t nq) {
 // re-run on the exact-order kernel.  Produces this shard's exact best-k keys (`local_keys` [nq][k]) or decoded results.
 int local_tensor(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, uint32_t nq, uint32_t k, cudaStream_t st,
                  uint64_t* local_keys, uint64_t* d_rows, float* d_scores, uint32_t* d_counts, int formula = CGVEC_FORMULA_SIMD) {
+    NvtxRange nvtx_("cgvec.tensor_scan");
     {
         int arc = ensure_smem_attr(tc_scan_kernel, kSmemBudget);
         if (!arc) arc = ensure_smem_attr(tc2_scan_kernel, kSmemBudget);
@@ -283,10 +284,27 @@ int tensor_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
     return exchange_and_decode(ix, c, local_keys, nq, k, 0, st, d_rows, d_scores, d_counts);
 }
 
-// AUTO's rule for sending a batch to the tensor kernels (rank-invariant on a sharded index).
+// AUTO's rule for sending a batch to the tensor kernels (rank-invariant on a sharded index: `rows` is the agreed smallest
+// shard).  Option tc_min_batch > 0 pins a fixed batch threshold (doubled for f32 storage); the default is a cost model fitted
+// to tools/bench_paths.py on a B200 (profiles/r02_exact_vs_tensor_small_batches.txt), in milliseconds:
+//   exact-order pass, 1 query   u = 0.03 + rows*dim*4 / 7.0e9   (f16 rows cost as much as f32: the kernel is bound by shared-memory
+//                                   wavefronts per element, not by bytes); 2 queries 1.12 u, 4 queries 1.63 u per launch
+//   tensor pass (<= n_max queries) 0.15 + rows*dim*esize / 6.6e9 + MMA time (matters beyond ~64 queries only)
+// Batch-1 always stays on the exact-order kernel (fully asynchronous, fused peer exchange, resident server).
+bool tensor_auto_rule(const Index* ix, uint64_t rows, uint32_t nq, uint32_t k, uint32_t n_max) {
+    if (rows < 4 * kTcCap || k > kTcCap / 16 || nq < 2 || n_max == 0) return false;
+    if (ix->opt_tc_min_nq > 0) return nq >= (ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq);
+    const double elems = (double)rows * ix->dim;
+    const double u = 0.03 + elems * 4.0 / 7.0e9;
+    const uint32_t n4 = nq / 4, r = nq % 4;
+    const double t_exact = n4 * 1.63 * u + (r == 3 ? 2.12 * u : r == 2 ? 1.12 * u : r == 1 ? u : 0.0);
+    const uint32_t passes = (nq + n_max - 1) / n_max;
+    const double mma_rate = ix->dtype == CGVEC_F32 ? 6.0e11 : 1.2e12;            // sustained flop per ms under the power cap
+    const double t_tensor = passes * (0.15 + elems * ix->esize / 6.6e9) + 2.0 * elems * nq / mma_rate;
+    return t_tensor < t_exact;
+}
 bool tensor_auto_ok(const Index* ix, int metric, uint32_t nq, uint32_t k) {
-    const uint32_t min_nq = ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq;
-    return tensor_path_applicable(ix, metric, nq) && nq >= min_nq && (ix->world > 1 ? ix->agreed_min_n : ix->n) >= 4 * kTcCap && k <= kTcCap / 16;
+    return tensor_path_applicable(ix, metric, nq) && tensor_auto_rule(ix, ix->world > 1 ? ix->agreed_min_n : ix->n, nq, k, tc_batch_limit(ix, nq));
 }
 
 // Runs nq queries (device, stride qstride) through whichever kernel family `path` selects, in batches.

@@ -298,6 +298,7 @@ int multi_search_formula(Index* mx, const float* queries, uint32_t nq, uint32_t 
 // Host I/O or device I/O (queries / results in the FIRST device's memory, asynchronous on the caller's stream).
 int multi_search(Index* mx, const float* queries, uint32_t nq, uint32_t k, const cgvec_search_opts& o, uint64_t* out_rows,
                  uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_counts) {
+    NvtxRange nvtx_("cgvec.multi_search");
     if (o.formula != CGVEC_FORMULA_SIMD) return multi_search_formula(mx, queries, nq, k, o, out_rows, out_ids, out_scores, out_counts);
     if (k > kMaxK) return fail(CGVEC_ERR_UNSUPPORTED, "k = %u exceeds the fused top-k limit of %u", k, kMaxK);
     const size_t G = mx->parts.size();
@@ -379,8 +380,7 @@ int multi_search(Index* mx, const float* queries, uint32_t nq, uint32_t k, const
         if (o.metric != CGVEC_COSINE) return finish(fail(CGVEC_ERR_UNSUPPORTED, "the tensor-core path serves the cosine metric"));
         tensor = true;
     } else if (o.path == CGVEC_PATH_AUTO) {
-        const uint32_t min_nq = p0->dtype == CGVEC_F32 ? (uint32_t)p0->opt_tc_min_nq * 2 : (uint32_t)p0->opt_tc_min_nq;
-        tensor = o.metric == CGVEC_COSINE && nq >= min_nq && min_n >= 4 * kTcCap && k <= kTcCap / 16;
+        tensor = o.metric == CGVEC_COSINE && tensor_auto_rule(p0, min_n, nq, k, tc_batch_limit(p0, nq));
     }
     uint32_t n_max = tensor ? tc_batch_limit(p0, nq) : 0;
     if (tensor && n_max == 0) {
