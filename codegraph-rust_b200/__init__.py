@@ -39,6 +39,8 @@ EXPORTS = [
     "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_multi_locate", "cgvec_multi_local_count", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
     "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_get_trace", "cgvec_last_error", "cgvec_version",
     "cgvec_stream_open", "cgvec_stream_submit", "cgvec_stream_flush", "cgvec_stream_close",
+    "cgvec_serve_open", "cgvec_serve_submit", "cgvec_serve_wait", "cgvec_serve_search", "cgvec_serve_pause", "cgvec_serve_stats",
+    "cgvec_serve_set", "cgvec_serve_close", "cgvec_serve_timer_start", "cgvec_serve_timer_stop",
 ]
 
 
@@ -123,6 +125,16 @@ def load_library(build: bool = True):
     L.cgvec_stream_submit.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, u32p]
     L.cgvec_stream_flush.argtypes = [vp, vp, vp, vp, u32p]
     L.cgvec_stream_close.argtypes = [vp]
+    L.cgvec_serve_open.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(vp)]
+    L.cgvec_serve_submit.argtypes = [vp, vp, C.c_int, vp, vp, vp, u32p]
+    L.cgvec_serve_wait.argtypes = [vp, C.c_uint32]
+    L.cgvec_serve_search.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cgvec_serve_pause.argtypes = [vp]
+    L.cgvec_serve_stats.argtypes = [vp, u64p, u64p]
+    L.cgvec_serve_set.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.cgvec_serve_close.argtypes = [vp]
+    L.cgvec_serve_timer_start.argtypes = [vp]
+    L.cgvec_serve_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.cgvec_last_error.restype = C.c_char_p
     L.cgvec_version.restype = C.c_char_p
     _lib = L
@@ -188,6 +200,87 @@ class QueryStream:
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             load_library().cgvec_stream_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ServeSession:
+    """cgvec_serve_*: batch-1 searches served by a RESIDENT scan kernel (no launch per query).  search() is the drop-in for
+    Index.search(q, k) with one query; submit_device()/wait() pipeline device-resident queries."""
+
+    def __init__(self, index: "Index", k: int, metric: int = COSINE, **options):
+        self._ix, self.k, self.metric = index, k, metric
+        self._h = C.c_void_p()
+        _check(load_library().cgvec_serve_open(index._h, k, metric, C.byref(self._h)))
+        for key, v in options.items():
+            self.set(key, v)
+        self._rows = np.empty(k, np.uint64); self._scores = np.empty(k, np.float32); self._count = np.zeros(1, np.uint32)
+        self._ids = np.zeros((k, 16), np.uint8)
+        self._p = (_ptr(self._rows), _ptr(self._ids), _ptr(self._scores), _ptr(self._count))
+        self._search = load_library().cgvec_serve_search
+        self._submit = load_library().cgvec_serve_submit
+        self._t = C.c_uint32(); self._tref = C.byref(self._t)
+        self.rows, self.scores, self.count = self._rows, self._scores, self._count
+
+    def set(self, key: str, value: int):
+        _check(load_library().cgvec_serve_set(self._h, key.encode(), int(value)))
+
+    def search(self, query, want_ids: bool = False):
+        """-> (rows u64[k], scores f32[k], count[, ids u8[k,16]]) — views of buffers reused by the next call"""
+        q = np.ascontiguousarray(query, np.float32).reshape(-1)
+        if q.shape[0] != self._ix.dim:
+            raise CgvecError(ERR_BAD_DIM, f"query dimension {q.shape[0]} != index dimension {self._ix.dim}")
+        rc = load_library().cgvec_serve_search(self._h, q.ctypes.data_as(C.c_void_p), self._p[0], self._p[1] if want_ids else None, self._p[2], self._p[3])
+        if rc:
+            _check(rc)
+        if want_ids:
+            return self._rows, self._scores, int(self._count[0]), self._ids
+        return self._rows, self._scores, int(self._count[0])
+
+    def search_raw(self, q: np.ndarray):
+        """search() without argument marshalling: `q` must be a C-contiguous float32 array of `dim` elements; results land in
+        self.rows / self.scores / self.count (the calling convention a server loop uses)."""
+        rc = self._search(self._h, q.ctypes.data, self._p[0], None, self._p[2], self._p[3])
+        if rc:
+            _check(rc)
+
+    def submit_device(self, d_query: int, d_rows: int, d_scores: int, d_counts: int) -> int:
+        """Device-resident query (qstride floats) and result buffers (raw device pointers); returns the ticket."""
+        rc = self._submit(self._h, d_query, 1, d_rows, d_scores, d_counts, self._tref)
+        if rc:
+            _check(rc)
+        return self._t.value
+
+    def wait(self, ticket: int):
+        rc = load_library().cgvec_serve_wait(self._h, ticket)
+        if rc:
+            _check(rc)
+
+    def pause(self):
+        _check(load_library().cgvec_serve_pause(self._h))
+
+    def timer_start(self):
+        """CUDA-event bracket on the session's launch stream (kernel launch, queries and kernel exit lie inside)."""
+        _check(load_library().cgvec_serve_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(load_library().cgvec_serve_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(load_library().cgvec_serve_stats(self._h, C.byref(a), C.byref(b)))
+        return {"launches": int(a.value), "served": int(b.value)}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            load_library().cgvec_serve_close(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

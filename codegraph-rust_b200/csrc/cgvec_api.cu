@@ -6,6 +6,7 @@
 // entry point returns CGVEC_ERR_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <cmath>
@@ -29,6 +30,7 @@
 #include "nccl_dyn.h"
 #include "scan_exact.cuh"
 #include "scan_i8.cuh"
+#include "scan_serve.cuh"
 #include "scan_tc.cuh"
 
 #define CGVEC_EXPORT extern "C" __attribute__((visibility("default")))
@@ -885,6 +887,7 @@ CGVEC_EXPORT int cgvec_search(const cgvec_index* ix, const float* queries, uint3
 }
 
 #include "stream_search.inl"
+#include "serve.inl"
 
 template <typename T>
 static void launch_rescore_t(Index* ix, const float* d_q, const uint64_t* d_local_rows, uint32_t n, int metric, int formula,

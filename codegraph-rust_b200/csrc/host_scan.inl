@@ -3,7 +3,8 @@
 // per-batch drivers local_exact / scan_batch.
 // ---- scan planning / launch ---------------------------------------------------------------------
 // `ld`, `esize`, `dim`, `n` default to the index's own matrix; the int8 scan passes its code matrix (words of 4 codes).
-int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g, uint32_t ld = 0, uint32_t esize = 0, uint32_t dim = 0, uint64_t n = ~0ull) {
+int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g, uint32_t ld = 0, uint32_t esize = 0, uint32_t dim = 0, uint64_t n = ~0ull,
+              uint32_t extra_smem = 0) {
     if (ld == 0) { ld = ix->ld; esize = ix->esize; dim = ix->dim; }
     if (n == ~0ull) n = ix->n;
     g->row_words = scan_row_words(ld, esize);
@@ -25,7 +26,7 @@ int plan_scan(const Index* ix, uint32_t k, uint32_t nq, ScanGeom* g, uint32_t ld
             uint32_t cand = next_pow2(k + sync * tile);
             if (cand < 64) cand = 64;
             ScanSmemLayout L = scan_smem_layout(g->row_words, tile, s, dim, nq, cand);
-            if (L.total > kSmemBudget) continue;
+            if (L.total + extra_smem > kSmemBudget) continue;   // extra_smem: what the caller appends behind this layout (resident server)
             uint32_t bytes = s * tile * g->row_words * 4;
             if (bytes > best_bytes + best_bytes / 8) {          // keep the first (preferred) tile unless another buffers >12% more
                 best_bytes = bytes;

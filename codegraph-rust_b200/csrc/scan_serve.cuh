@@ -29,9 +29,10 @@ namespace cgv {
 
 constexpr int kServeConsumerWarps = 8;
 constexpr int kServeConsumerThreads = 32 * kServeConsumerWarps;
-constexpr int kServeThreads = 32 * (kServeConsumerWarps + 2);      // + producer warp (8) + poller warp (9, CTA 0 only)
+constexpr int kServeThreads = 32 * (kServeConsumerWarps + 3);      // + producer (8), helper (9) and poller (10, CTA 0 only) warps
 constexpr uint32_t kServeSlots = 8;                                // descriptor ring depth = most queries in flight
 constexpr uint32_t kServeMaxK = 64;
+constexpr uint32_t kServeMaxGrid = 192;                            // CTAs of a session (one per SM)
 constexpr uint32_t kServeMarkEnd = 0xffffffffu, kServeMarkEmpty = 0xfffffffeu;
 
 struct ServeDesc {                   // one submitted query; written by the host BEFORE the doorbell is bumped
@@ -59,9 +60,13 @@ struct ServeCtrl {                   // device memory, reset by the host before 
     uint32_t go;                     // highest sequence number published to the CTAs
     uint32_t exit_seq;               // 0 while running, else the first sequence number this launch does not serve
     uint32_t completed;              // highest sequence number finalised
-    uint32_t pad[3];
+    uint32_t pass_done;              // producers that have finished issuing a pass over the shard (lockstep option), summed over passes
+    uint32_t pad[2];
     uint32_t done[kServeSlots];      // lists delivered, per sequence slot
     ServeDesc ddesc[kServeSlots];    // device copy of the descriptors (q_ptr already pointing into device memory)
+    // One 128-byte line per CTA: [0] = go, [1] = exit_seq as seen by THAT CTA's helper warp.  148 helpers polling one word
+    // would make a hot spot of a single L2 slice — and every TMA row load of the scan crosses every slice.
+    uint32_t cta_line[kServeMaxGrid][32];
 };
 
 struct ServeParams {
@@ -70,6 +75,9 @@ struct ServeParams {
     uint32_t chunk_tiles;            // row tiles per ticket (multiple of the group count)
     uint32_t start_seq;              // first sequence number this launch serves
     uint32_t off_tile, off_ctl, off_merge, smem_total;   // extra shared-memory regions behind K1's layout
+    uint32_t merge_lists;            // per-CTA lists the finishing CTA stages at once (multiple of 32, <= 256)
+    uint32_t lockstep;               // (unused)
+    uint32_t contig;                 // 1: every CTA streams one contiguous run of row tiles instead of K1's interleaved ones
     ServeCtrl* ctrl;
     ServeHostBlock* host;            // device pointer of the mapped block
     float* qbuf;                     // [kServeSlots][qstride] device staging of host-resident queries
@@ -98,29 +106,62 @@ __device__ __forceinline__ uint32_t lds_volatile(const uint32_t* p) {
 }
 __device__ __forceinline__ void sts_volatile(uint32_t* p, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 // watchdog of every spin in this kernel: a bug or a dead peer must end in a failed launch, never in a wedged GPU
+// (%globaltimer is read only every 16384 spins: `t0` starts as 0 and is latched at the first check, so a wait that succeeds at
+// once — every stage of the steady-state stream — never touches the timer)
 #define CGV_SERVE_SPIN_GUARD(spins, t0, limit)                                             \
-    if (((++(spins)) & 0x3fffu) == 0u && global_ns() - (t0) > (limit)) { __trap(); }
+    if (((++(spins)) & 0x3fffu) == 0u) {                                                   \
+        const uint64_t now_ = global_ns();                                                 \
+        if ((t0) == 0ull) (t0) = now_;                                                     \
+        else if (now_ - (t0) > (limit)) { __trap(); }                                      \
+    }
 
-enum : uint32_t { kServeRun = 1, kServeExit = 2 };
+// A warp-wide bitonic sort (descending) of n = 2^m keys in shared memory.
+__device__ __forceinline__ void serve_warp_sort_desc(uint64_t* s, uint32_t n, uint32_t lane) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = lane; i < (n >> 1); i += 32) {
+                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = s[lo], b = s[hi];
+                if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
 
+// Shared-memory control words behind the mbarriers of the session (s_ctl[])
+enum : uint32_t { kCtlExit = 0, kCtlProdDone = 1, kCtlIssued = 2, kCtlWords = 8 };
+
+// Warp roles: 0-7 consumers, 8 producer, 9 helper (query prefetch, end-of-query sort / hand-over / finish), 10 poller (CTA 0).
+//
+// Per query the CONSUMERS only flip buffers: the query (and its squared norm, in the reference's order) was put into the other
+// query buffer by the helper while the previous query was being scanned; at the end marker they leave their unsorted
+// candidates in the current candidate buffer for the helper and move on to the next query's stages, which the producer has
+// been streaming all along (static tile assignment blockIdx + i*grid, exactly K1's).  The HELPER sorts the candidates, writes
+// the CTA's list, counts it in, and — on the CTA that delivered the last list of the query — merges all lists, runs the peer
+// exchange, decodes into the submitter's buffers and publishes the completion.  None of that is on the scan's critical path.
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(kServeThreads, 1) scan_serve_kernel(const ServeParams P) {
     extern __shared__ __align__(128) uint8_t smem_sv[];
     const ScanParams& p = P.sp;
     uint8_t* smem = smem_sv;
-    const ScanSmemLayout lay = scan_smem_layout(p.row_words, p.tile_rows, p.stages, p.d, 1, p.cand_cap);
+    const ScanSmemLayout lay = scan_smem_layout(p.row_words, p.tile_rows, p.stages, p.d, 2, p.cand_cap);   // two query / candidate buffers
     uint8_t* s_rows = smem + lay.off_rows;
     float* s_norms = reinterpret_cast<float*>(smem + lay.off_norms);
-    float* s_q = reinterpret_cast<float*>(smem + lay.off_q);
-    uint64_t* s_cand = reinterpret_cast<uint64_t*>(smem + lay.off_cand);
+    float* s_q = reinterpret_cast<float*>(smem + lay.off_q);                    // [2][qstride]
+    uint64_t* s_cand = reinterpret_cast<uint64_t*>(smem + lay.off_cand);        // [2][cand_cap]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
     uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* s_thr = reinterpret_cast<uint64_t*>(smem + lay.off_misc);
-    uint32_t* s_count = reinterpret_cast<uint32_t*>(smem + lay.off_misc + 8);
-    uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem + P.off_tile);          // [stages] row tile of the stage, or a marker
-    uint32_t* s_ctl = reinterpret_cast<uint32_t*>(smem + P.off_ctl);            // [0] consumer broadcast, [1] exit request to the producer,
-                                                                                // [2] producer stopped, [3] stages issued in total (lo), [4] last-list flag
-    uint64_t* s_merge = reinterpret_cast<uint64_t*>(smem + P.off_merge);        // [grid*k | 8*k | k]
+    uint64_t* s_thr = reinterpret_cast<uint64_t*>(smem + lay.off_misc);         // [2]
+    uint32_t* s_count = reinterpret_cast<uint32_t*>(smem + lay.off_misc + 16);  // [2]
+    uint64_t* q_ready = reinterpret_cast<uint64_t*>(smem + P.off_ctl);          // [2] helper -> consumers: query buffer filled
+    uint64_t* q_free = q_ready + 2;                                             // [2] consumers -> helper: query buffer no longer read
+    uint64_t* cand_full = q_free + 2;                                           // [2] consumers -> helper: candidates of the query complete
+    uint64_t* cand_free = cand_full + 2;                                        // [2] helper -> consumers: candidate buffer reset
+    uint32_t* s_ctl = reinterpret_cast<uint32_t*>(cand_free + 2);               // [kCtlWords]
+    float* s_na = reinterpret_cast<float*>(s_ctl + kCtlWords);                  // [2] squared query norms
+    uint64_t* s_merge = reinterpret_cast<uint64_t*>(smem + P.off_merge);        // [merge_lists*k | 8*k | k]
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t warps_per_stage = p.tile_rows >> 2;
@@ -130,18 +171,23 @@ __global__ void __launch_bounds__(kServeThreads, 1) scan_serve_kernel(const Serv
     const uint32_t row_bytes = p.ld * sizeof(T);
     const bool ascending = (METRIC == METRIC_L2);
     const uint64_t num_tiles = (p.n_rows + p.tile_rows - 1) / p.tile_rows;
-    const uint64_t chunks_per_q = (num_tiles + P.chunk_tiles - 1) / P.chunk_tiles;
+    // Tile assignment: interleaved (CTA c takes tiles c, c + grid, ... — K1's) or, option `contig`, one contiguous run per CTA.
+    const uint64_t per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+    const uint64_t my_tiles = P.contig ? (num_tiles > blockIdx.x * per_cta ? min(per_cta, num_tiles - blockIdx.x * per_cta) : 0)
+                                       : ((num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    const uint64_t tile_base = P.contig ? blockIdx.x * per_cta : blockIdx.x, tile_step = P.contig ? 1 : gridDim.x;
     const uint64_t t_launch = global_ns();
 
     if (tid == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], warps_per_stage); }
-        s_thr[0] = 0; s_count[0] = 0;
-        for (int i = 0; i < 8; ++i) s_ctl[i] = 0;
+        for (int i = 0; i < 8; ++i) mbar_init(&q_ready[i], 1);
+        s_thr[0] = 0; s_thr[1] = 0; s_count[0] = 0; s_count[1] = 0;
+        for (uint32_t i = 0; i < kCtlWords; ++i) s_ctl[i] = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (warp == kServeConsumerWarps + 1) {
+    if (warp == kServeConsumerWarps + 2) {
         // ===================== poller (CTA 0): host doorbell -> device-wide "go" =====================
         if (blockIdx.x != 0) return;
         uint32_t pub = P.start_seq - 1;
@@ -153,16 +199,22 @@ __global__ void __launch_bounds__(kServeThreads, 1) scan_serve_kernel(const Serv
             if ((int32_t)(db - pub) > 0) {
                 for (uint32_t s = pub + 1; (int32_t)(db - s) >= 0; ++s) {
                     const uint32_t slot = s % kServeSlots;
-                    // the descriptor: 16 words, one per lane
-                    uint32_t w = 0;
+                    uint32_t w = 0;                              // the descriptor: 16 words, one per lane
                     if (lane < 16) w = ld_volatile_sys(reinterpret_cast<const volatile uint32_t*>(&P.host->desc[slot]) + lane);
                     const uint32_t q_lo = __shfl_sync(0xffffffffu, w, 0), q_hi = __shfl_sync(0xffffffffu, w, 1);
                     const uint32_t on_host = __shfl_sync(0xffffffffu, w, 8);
                     uint64_t q_ptr = ((uint64_t)q_hi << 32) | q_lo;
                     if (on_host) {                               // stage the query into device memory: every CTA reads it from L2
-                        const float* src = reinterpret_cast<const float*>(q_ptr);
-                        float* dst = P.qbuf + (size_t)slot * qstride;
-                        for (uint32_t i = lane; i < qstride; i += 32) dst[i] = __ldcv(src + i);
+                        const float4* src = reinterpret_cast<const float4*>(q_ptr);
+                        float4* dst = reinterpret_cast<float4*>(P.qbuf + (size_t)slot * qstride);
+                        const uint32_t n4 = qstride >> 2;
+                        for (uint32_t i0 = 0; i0 < n4; i0 += 128) {          // 4 x 16-byte PCIe reads in flight per lane
+                            float4 v[4];
+#pragma unroll
+                            for (uint32_t u = 0; u < 4; ++u) { const uint32_t i = i0 + u * 32 + lane; v[u] = i < n4 ? __ldcv(src + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                            for (uint32_t u = 0; u < 4; ++u) { const uint32_t i = i0 + u * 32 + lane; if (i < n4) dst[i] = v[u]; }
+                        }
                         q_ptr = reinterpret_cast<uint64_t>(dst);
                     }
                     uint32_t* dd = reinterpret_cast<uint32_t*>(&P.ctrl->ddesc[slot]);
@@ -172,12 +224,18 @@ __global__ void __launch_bounds__(kServeThreads, 1) scan_serve_kernel(const Serv
                     __threadfence();
                     __syncwarp();
                     if (lane == 0) st_release_gpu(&P.ctrl->go, s);
+                    for (uint32_t c = lane; c < gridDim.x; c += 32) st_release_gpu(&P.ctrl->cta_line[c][0], s);
                 }
                 pub = db;
                 t_idle = global_ns();
             } else {
                 const uint64_t now = global_ns();
-                if (stop || now - t_idle > P.idle_ns || now - t_launch > P.life_ns) {
+                uint32_t comp = 0;
+                if (lane == 0) comp = ld_acquire_gpu(&P.ctrl->completed);
+                comp = __shfl_sync(0xffffffffu, comp, 0);
+                if (comp != pub) t_idle = now;                   // work in flight is not idleness
+                if ((stop && comp == pub) || now - t_idle > P.idle_ns || (now - t_launch > P.life_ns && comp == pub)) {
+                    for (uint32_t c = lane; c < gridDim.x; c += 32) st_release_gpu(&P.ctrl->cta_line[c][1], pub + 1);
                     if (lane == 0) {
                         st_release_gpu(&P.ctrl->exit_seq, pub + 1);
                         __threadfence_system();
@@ -191,267 +249,290 @@ __global__ void __launch_bounds__(kServeThreads, 1) scan_serve_kernel(const Serv
     }
 
     if (warp == kServeConsumerWarps) {
-        // ===================== producer: query-agnostic row stream =====================
+        // ===================== producer: the row stream, round and round (K1's static tile assignment) =====================
         const uint64_t policy = l2_policy_evict_first();
         uint64_t n = 0;                                          // stages posted
-        uint32_t cur_q = P.start_seq;                            // oldest query whose end marker is still to be posted
         bool stopped = false;
-        // waits for stage slot (n % stages) to be free; false = the consumers asked us to stop
-        auto slot_free = [&]() -> bool {
+        auto slot_free = [&]() -> bool {                         // false = the session is ending
             const uint32_t s = (uint32_t)(n % p.stages);
             if (n >= p.stages) {
                 const uint32_t par = (uint32_t)(((n / p.stages) - 1) & 1);
                 uint32_t spins = 0;
-                const uint64_t t0 = global_ns();
+                uint64_t t0 = 0;
                 while (!mbar_try_wait(&empty_bar[s], par)) {
-                    if (lds_volatile(&s_ctl[1])) return false;
+                    if (lds_volatile(&s_ctl[kCtlExit])) return false;
                     CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns)
                 }
             }
-            return lds_volatile(&s_ctl[1]) == 0;
+            return lds_volatile(&s_ctl[kCtlExit]) == 0;
         };
-        auto post_marker = [&](uint32_t marker) -> bool {
-            if (!slot_free()) return false;
+        // Stage n of this CTA carries tile blockIdx + (n mod my_tiles) * grid: the consumers derive the query and the tile of a
+        // stage from its number alone, so nothing but rows travels through the ring.
+        uint64_t i = 0;                                          // tile index within the current pass
+        while (!stopped && my_tiles) {
+            if (!slot_free()) { stopped = true; break; }
             const uint32_t s = (uint32_t)(n % p.stages);
-            if (lane == 0) { sts_volatile(&s_tile[s], marker); mbar_arrive(&full_bar[s]); }
+            const uint64_t tile = tile_base + i * tile_step;
+            const uint64_t row0 = tile * p.tile_rows;
+            const uint32_t rows = (uint32_t)min((uint64_t)p.tile_rows, p.n_rows - row0);
+            const bool with_norms = (METRIC == METRIC_COSINE);
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes + (with_norms ? p.tile_rows * 4 : 0));
             __syncwarp();
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rows) + row0 * row_bytes;
+            uint8_t* dst = s_rows + (size_t)s * stage_bytes;
+            for (uint32_t r = lane; r < rows; r += 32) {
+                if (p.use_l2_hint) bulk_g2s_hint(dst + (size_t)r * p.row_words * 4, src + (size_t)r * row_bytes, row_bytes, &full_bar[s], policy);
+                else bulk_g2s(dst + (size_t)r * p.row_words * 4, src + (size_t)r * row_bytes, row_bytes, &full_bar[s]);
+            }
+            if (with_norms && lane == 0) bulk_g2s(s_norms + s * 32, p.norms + row0, p.tile_rows * 4, &full_bar[s]);
             ++n;
-            return true;
-        };
-        auto claim = [&]() -> unsigned long long {
-            unsigned long long t = 0;
-            if (lane == 0) t = atomicAdd(&P.ctrl->ticket, 1ull);
-            return __shfl_sync(0xffffffffu, t, 0);
-        };
-        unsigned long long tk = claim();
-        while (!stopped) {
-            const unsigned long long tk_next = claim();          // its round trip hides behind this chunk
-            const uint32_t q_t = P.start_seq + (uint32_t)(tk / chunks_per_q);
-            const uint64_t chunk = tk % chunks_per_q;
-            while (cur_q != q_t && !stopped) {                   // close every query older than this ticket's (also ones we got no chunk of)
-                while ((n % ngroups) && !stopped) stopped = !post_marker(kServeMarkEmpty);
-                for (uint32_t g = 0; g < ngroups && !stopped; ++g) stopped = !post_marker(kServeMarkEnd);
-                ++cur_q;
-            }
-            const uint64_t tile0 = chunk * P.chunk_tiles;
-            for (uint32_t c = 0; c < P.chunk_tiles && !stopped; ++c) {
-                const uint64_t tile = tile0 + c;
-                if (tile >= num_tiles) { stopped = !post_marker(kServeMarkEmpty); continue; }   // keeps chunks group-aligned
-                if (!slot_free()) { stopped = true; break; }
-                const uint32_t s = (uint32_t)(n % p.stages);
-                const uint64_t row0 = tile * p.tile_rows;
-                const uint32_t rows = (uint32_t)min((uint64_t)p.tile_rows, p.n_rows - row0);
-                const bool with_norms = (METRIC == METRIC_COSINE);
-                if (lane == 0) {
-                    sts_volatile(&s_tile[s], (uint32_t)tile);
-                    mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes + (with_norms ? p.tile_rows * 4 : 0));
-                }
-                __syncwarp();
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rows) + row0 * row_bytes;
-                uint8_t* dst = s_rows + (size_t)s * stage_bytes;
-                for (uint32_t r = lane; r < rows; r += 32)
-                    bulk_g2s_hint(dst + (size_t)r * p.row_words * 4, src + (size_t)r * row_bytes, row_bytes, &full_bar[s], policy);
-                if (with_norms && lane == 0) bulk_g2s(s_norms + s * 32, p.norms + row0, p.tile_rows * 4, &full_bar[s]);
-                ++n;
-            }
-            tk = tk_next;
+            if (++i == my_tiles) i = 0;
         }
-        if (lane == 0) { sts_volatile(&s_ctl[3], (uint32_t)n); __threadfence_block(); sts_volatile(&s_ctl[2], 1u); }
+        if (!my_tiles) {                                         // a CTA without rows only waits for the end of the session
+            uint32_t spins = 0;
+            uint64_t t0 = 0;
+            while (lds_volatile(&s_ctl[kCtlExit]) == 0u) { __nanosleep(1000); CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
+        }
+        if (lane == 0) { sts_volatile(&s_ctl[kCtlIssued], (uint32_t)n); __threadfence_block(); sts_volatile(&s_ctl[kCtlProdDone], 1u); }
         return;
     }
 
-    // ===================== consumers: exact-order scoring, candidate filter, per-query hand-over =====================
+    if (warp == kServeConsumerWarps + 1) {
+        // ===================== helper: query prefetch, end-of-query sort + hand-over, finishing a query =====================
+        uint32_t jf = 0, jp = 0;                                 // queries fetched / post-processed by this CTA (index from start_seq)
+        uint32_t go_seen = P.start_seq - 1, ex_seen = 0;         // last values read from this CTA's publication line
+        const uint32_t* my_line = P.ctrl->cta_line[blockIdx.x];
+        uint32_t spins = 0;
+        uint64_t t0 = 0;
+        while (true) {
+            bool progressed = false;
+            // ---- (1) the consumers have finished query jp: sort, deliver, maybe finish
+            if (jp < jf && mbar_try_wait(&cand_full[jp & 1], (jp >> 1) & 1)) {
+                const uint32_t b = jp & 1, seq = P.start_seq + jp, slot = seq % kServeSlots;
+                uint64_t* cand = s_cand + (size_t)b * p.cand_cap;
+                const uint32_t cnt = min(lds_volatile(&s_count[b]), p.cand_cap);
+                for (uint32_t i = cnt + lane; i < p.cand_cap; i += 32) cand[i] = 0ull;
+                __syncwarp();
+                serve_warp_sort_desc(cand, p.cand_cap, lane);
+                uint64_t* out = P.lists + ((size_t)slot * gridDim.x + blockIdx.x) * p.k;
+                for (uint32_t i = lane; i < p.k; i += 32) out[i] = (i < cnt) ? cand[i] : 0ull;
+                __threadfence();
+                __syncwarp();
+                uint32_t last = 0;
+                if (lane == 0) {
+                    last = atomicAdd(&P.ctrl->done[slot], 1u) == gridDim.x - 1 ? 1u : 0u;
+                    s_count[b] = 0; s_thr[b] = 0ull;
+                    mbar_arrive(&cand_free[b]);                  // the consumers may reuse this candidate buffer
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    {   // queries are finished in order (the exchange's two-parity slots and the host's completion word rely on it)
+                        uint32_t sp = 0;
+                        uint64_t tw = 0;
+                        while ((int32_t)(ld_acquire_gpu(&P.ctrl->completed) + 1 - seq) < 0) { CGV_SERVE_SPIN_GUARD(sp, tw, P.abort_ns) }
+                    }
+                    const uint32_t n_lists = gridDim.x;
+                    uint64_t* staged = s_merge;                  // [merge_lists * k]
+                    uint64_t* lvl = s_merge + (size_t)P.merge_lists * p.k;   // [8][k] winners of every group of 32 lists
+                    uint64_t* best = lvl + 8 * p.k;              // [k]
+                    const uint64_t* src = P.lists + (size_t)slot * gridDim.x * p.k;
+                    const uint32_t nw = (n_lists + 31) / 32;
+                    for (uint32_t l0 = 0; l0 < n_lists; l0 += P.merge_lists) {
+                        const uint32_t ln = min(P.merge_lists, n_lists - l0), tot = ln * p.k;
+                        for (uint32_t i0 = 0; i0 < tot; i0 += 512) {             // 16 loads in flight per lane
+                            uint64_t v[16];
+#pragma unroll
+                            for (uint32_t u = 0; u < 16; ++u) { const uint32_t i = i0 + u * 32 + lane; v[u] = i < tot ? __ldcg(src + (size_t)l0 * p.k + i) : 0ull; }
+#pragma unroll
+                            for (uint32_t u = 0; u < 16; ++u) { const uint32_t i = i0 + u * 32 + lane; if (i < tot) staged[i] = v[u]; }
+                        }
+                        __syncwarp();
+                        for (uint32_t g = 0; g * 32 < ln; ++g) {
+                            warp_tournament_topk(staged + (size_t)g * 32 * p.k, min(32u, ln - g * 32), p.k, p.k, p.k, lvl + (size_t)(l0 / 32 + g) * p.k, lane);
+                            __syncwarp();
+                        }
+                    }
+                    warp_tournament_topk(lvl, nw, p.k, p.k, p.k, best, lane);
+                    __syncwarp();
+                    const ServeDesc* dd = &P.ctrl->ddesc[slot];
+                    if (P.world > 1) {
+                        // the peer exchange of exchange.cuh, executed by this warp: push, publish, wait, gather, merge
+                        const uint32_t xseq = __ldcg(&dd->xseq), parity = xseq & 1u;
+                        for (uint32_t i = lane; i < P.world * p.k; i += 32) {
+                            const uint32_t r = i / p.k, j = i - r * p.k;
+                            xchg_slot(P.peer[r], parity, P.rank, 0)[j] = best[j];
+                        }
+                        __threadfence_system();
+                        __syncwarp();
+                        if (lane < P.world) st_release_sys(&xchg_flags(P.peer[lane])[P.rank * kXchgMaxQ], xseq);
+                        if (lane < P.world) {
+                            const uint32_t* f = &xchg_flags(P.peer[P.rank])[lane * kXchgMaxQ];
+                            const uint64_t tw = global_ns();
+                            uint32_t sp = 0;
+                            while ((int32_t)(ld_acquire_sys(f) - xseq) < 0) {
+                                if ((++sp & 1023u) == 0 && global_ns() - tw > P.xchg_timeout_ns) { atomicExch_system(const_cast<uint32_t*>(&P.host->error), 1u + lane); break; }
+                            }
+                        }
+                        __syncwarp();
+                        for (uint32_t i = lane; i < P.world * p.k; i += 32) {
+                            const uint32_t r = i / p.k, j = i - r * p.k;
+                            staged[i] = __ldcg(xchg_slot(P.peer[P.rank], parity, r, 0) + j);
+                        }
+                        __syncwarp();
+                        warp_tournament_topk(staged, P.world, p.k, p.k, p.k, best, lane);
+                        __syncwarp();
+                    }
+                    uint64_t* o_rows = reinterpret_cast<uint64_t*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->out_rows)));
+                    float* o_scores = reinterpret_cast<float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->out_scores)));
+                    uint32_t* o_counts = reinterpret_cast<uint32_t*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->out_counts)));
+                    uint32_t valid_n = 0;
+                    for (uint32_t i = lane; i < p.k; i += 32) {
+                        const uint64_t key = best[i];
+                        const bool valid = key != 0ull;
+                        if (o_rows) o_rows[i] = valid ? (uint64_t)key_row(key) : ~0ull;
+                        if (o_scores) o_scores[i] = valid ? key_score(key, ascending) : 0.0f;
+                        valid_n += valid;
+                    }
+                    valid_n = __reduce_add_sync(0xffffffffu, valid_n);
+                    if (lane == 0 && o_counts) *o_counts = valid_n;
+                    __threadfence_system();
+                    __syncwarp();
+                    if (lane == 0) {
+                        P.ctrl->done[slot] = 0;
+                        __threadfence_system();
+                        st_release_gpu(&P.ctrl->completed, seq);
+                        st_release_sys(const_cast<uint32_t*>(&P.host->completed), seq);
+                    }
+                    __syncwarp();
+                }
+                ++jp;
+                progressed = true;
+            }
+            // ---- (2) the next query has been published and its buffer is free: fetch it, compute its squared norm
+            if (jf - jp < 2) {
+                const uint32_t seq = P.start_seq + jf, b = jf & 1;
+                if ((int32_t)(go_seen - seq) < 0) {              // poll L2 only while the next query is not known to be published
+                    uint32_t go = 0, ex = 0;
+                    if (lane == 0) { go = ld_acquire_gpu(my_line); ex = ld_acquire_gpu(my_line + 1); }
+                    go_seen = __shfl_sync(0xffffffffu, go, 0); ex_seen = __shfl_sync(0xffffffffu, ex, 0);
+                }
+                const uint32_t go = go_seen, ex = ex_seen;
+                if ((int32_t)(go - seq) >= 0) {
+                    if (mbar_try_wait(&q_free[b], ((jf >> 1) & 1) ^ 1)) {
+                        const ServeDesc* dd = &P.ctrl->ddesc[seq % kServeSlots];
+                        const float4* q = reinterpret_cast<const float4*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->q_ptr)));
+                        float4* dst = reinterpret_cast<float4*>(s_q + (size_t)b * qstride);
+                        const uint32_t n4 = qstride >> 2;
+                        for (uint32_t i0 = 0; i0 < n4; i0 += 256) {
+                            float4 v[8];
+#pragma unroll
+                            for (uint32_t u = 0; u < 8; ++u) { const uint32_t i = i0 + u * 32 + lane; v[u] = i < n4 ? __ldcg(q + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                            for (uint32_t u = 0; u < 8; ++u) { const uint32_t i = i0 + u * 32 + lane; if (i < n4) dst[i] = v[u]; }
+                        }
+                        __syncwarp();
+                        const float na = (METRIC == METRIC_COSINE) ? sqnorm_octet(s_q + (size_t)b * qstride, p.d, (int)(lane & 7)) : 0.0f;
+                        if (lane == 0) { s_na[b] = na; mbar_arrive(&q_ready[b]); }
+                        __syncwarp();
+                        ++jf;
+                        progressed = true;
+                    }
+                } else if (ex != 0 && (int32_t)(seq - ex) >= 0 && jp == jf) {
+                    if (lane == 0) sts_volatile(&s_ctl[kCtlExit], 1u);      // nothing more will be published to this launch
+                    break;
+                }
+            }
+            if (progressed) { spins = 0; t0 = 0; }
+            else { __nanosleep(400); CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
+        }
+        return;
+    }
+
+    // ===================== consumers: exact-order scoring and candidate filter =====================
     const uint32_t group = warp / warps_per_stage, sub = warp % warps_per_stage;
     const uint32_t ctid = tid, nct = kServeConsumerThreads;
     const int L = lane & 7;
     const uint32_t lrow = sub * 4 + (lane >> 3);
-    const uint32_t flush_limit = p.cand_cap - P.epoch_rounds * ngroups * p.tile_rows;
+    const uint32_t epoch_tiles = P.epoch_rounds * ngroups;                      // tiles between threshold syncs (K1's sync_interval)
+    const uint32_t flush_limit = p.cand_cap - epoch_tiles * p.tile_rows;
 
-    auto sync_and_maybe_compact = [&](bool force) {
-        named_bar_sync(1, nct);
-        const uint32_t cnt = s_count[0];
-        named_bar_sync(1, nct);
-        if (force || cnt > flush_limit) {
-            for (uint32_t i = cnt + ctid; i < p.cand_cap; i += nct) s_cand[i] = 0;
-            named_bar_sync(1, nct);
-            bitonic_sort_desc(s_cand, p.cand_cap, ctid, nct, 1);
-            if (ctid == 0) {
-                const uint32_t keep = min(cnt, p.k);
-                s_count[0] = keep;
-                s_thr[0] = (keep >= p.k) ? s_cand[p.k - 1] : 0ull;
-            }
-            named_bar_sync(1, nct);
-        }
-    };
-
-    uint64_t n = group;                                          // next stage of my group
-    uint32_t cur = P.start_seq;
-    while (true) {
-        // ---- wait until query `cur` is published (and the query two before it is out of the way), or for the exit decision
-        if (ctid == 0) {
-            uint32_t spins = 0, flag = 0;
-            const uint64_t t0 = global_ns();
-            while (true) {
-                const uint32_t go = ld_acquire_gpu(&P.ctrl->go);
-                if ((int32_t)(go - cur) >= 0) {
-                    const uint32_t comp = ld_acquire_gpu(&P.ctrl->completed);
-                    if ((int32_t)(comp + 2 - cur) >= 0) { flag = kServeRun; break; }
-                } else {
-                    const uint32_t ex = ld_acquire_gpu(&P.ctrl->exit_seq);
-                    if (ex != 0 && (int32_t)(cur - ex) >= 0) { flag = kServeExit; break; }
-                }
+    uint64_t n = group;                                          // next stage of my group (stage numbers run on across queries)
+    for (uint32_t j = 0;; ++j) {
+        const uint32_t b = j & 1;
+        uint64_t* cand = s_cand + (size_t)b * p.cand_cap;
+        {   // the query buffer is filled and the candidate buffer reset, or the session is over
+            uint32_t spins = 0;
+            uint64_t t0 = 0;
+            bool leave = false;
+            while (!mbar_try_wait(&q_ready[b], (j >> 1) & 1)) {
+                if (lds_volatile(&s_ctl[kCtlExit])) { leave = true; break; }
                 CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns)
             }
-            sts_volatile(&s_ctl[0], flag);
+            if (leave) break;
+            while (!mbar_try_wait(&cand_free[b], ((j >> 1) & 1) ^ 1)) { CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
         }
-        named_bar_sync(1, nct);
-        const uint32_t flag = lds_volatile(&s_ctl[0]);
-        if (flag != kServeRun) break;
-        const uint32_t slot = cur % kServeSlots;
-        {
-            const ServeDesc* dd = &P.ctrl->ddesc[slot];
-            const float* q = reinterpret_cast<const float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->q_ptr)));
-            for (uint32_t i = ctid; i < qstride; i += nct) s_q[i] = __ldcg(q + i);
-            if (ctid == 0) { s_thr[0] = 0; s_count[0] = 0; }
-        }
-        named_bar_sync(1, nct);
-        float na = (METRIC == METRIC_COSINE) ? sqnorm_octet(s_q, p.d, L) : 0.0f;
-        na = __shfl_sync(0xffffffffu, na, lane & ~7);
+        const float* qv = s_q + (size_t)b * qstride;
+        const float na = s_na[b];
 
-        // ---- my group's stages of this query, up to its end marker
-        uint32_t rounds = 0;
-        while (true) {
+        auto sync_and_maybe_compact = [&]() {
+            named_bar_sync(1, nct);
+            const uint32_t cnt = s_count[b];
+            named_bar_sync(1, nct);
+            if (cnt > flush_limit) {
+                for (uint32_t i = cnt + ctid; i < p.cand_cap; i += nct) cand[i] = 0;
+                named_bar_sync(1, nct);
+                bitonic_sort_desc(cand, p.cand_cap, ctid, nct, 1);
+                if (ctid == 0) {
+                    const uint32_t keep = min(cnt, p.k);
+                    s_count[b] = keep;
+                    s_thr[b] = (keep >= p.k) ? cand[p.k - 1] : 0ull;
+                }
+                named_bar_sync(1, nct);
+            }
+        };
+
+        // my group's stages of query j: global stage numbers [j * my_tiles, (j + 1) * my_tiles) congruent to `group`
+        const uint64_t q_begin = (uint64_t)j * my_tiles, q_end = q_begin + my_tiles;
+        uint64_t next_boundary = epoch_tiles;                    // threshold syncs happen at the same local tile indices in every group
+        for (; n < q_end; n += ngroups) {
+            const uint64_t i = n - q_begin;                      // tile index within this pass
+            while (next_boundary <= i) { sync_and_maybe_compact(); next_boundary += epoch_tiles; }
             const uint32_t s = (uint32_t)(n % p.stages);
             {
                 uint32_t spins = 0;
-                const uint64_t t0 = global_ns();
+                uint64_t t0 = 0;
                 const uint32_t par = (uint32_t)((n / p.stages) & 1);
                 while (!mbar_try_wait(&full_bar[s], par)) { CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
             }
-            const uint32_t mark = lds_volatile(&s_tile[s]);
-            if (mark == kServeMarkEnd || mark == kServeMarkEmpty) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                n += ngroups;
-                if (mark == kServeMarkEnd) break;
-            } else {
-                const uint64_t row = (uint64_t)mark * p.tile_rows + lrow;
-                const T* rp = reinterpret_cast<const T*>(s_rows + (size_t)s * stage_bytes + (size_t)lrow * p.row_words * 4);
-                const float nb = (METRIC == METRIC_COSINE) ? s_norms[s * 32 + lrow] : 0.0f;
-                float sc[1];
-                score_row_octet<T, METRIC, 1>(rp, s_q, qstride, p.d, L, &na, nb, sc);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                if (L == 0 && row < p.n_rows) {
-                    const uint64_t key = make_key(sc[0], (uint32_t)scan_global_row(p, row), ascending);
-                    if (key > *reinterpret_cast<volatile uint64_t*>(&s_thr[0])) {
-                        const uint32_t pos = atomicAdd(&s_count[0], 1u);
-                        s_cand[pos] = key;
-                    }
+            const uint64_t tile = tile_base + i * tile_step;
+            const uint64_t row = tile * p.tile_rows + lrow;
+            const T* rp = reinterpret_cast<const T*>(s_rows + (size_t)s * stage_bytes + (size_t)lrow * p.row_words * 4);
+            const float nb = (METRIC == METRIC_COSINE) ? s_norms[s * 32 + lrow] : 0.0f;
+            float sc[1];
+            score_row_octet<T, METRIC, 1>(rp, qv, qstride, p.d, L, &na, nb, sc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (L == 0 && row < p.n_rows) {
+                const uint64_t key = make_key(sc[0], (uint32_t)scan_global_row(p, row), ascending);
+                if (key > *reinterpret_cast<volatile uint64_t*>(&s_thr[b])) {
+                    const uint32_t pos = atomicAdd(&s_count[b], 1u);
+                    cand[pos] = key;
                 }
-                n += ngroups;
             }
-            if (++rounds % P.epoch_rounds == 0) sync_and_maybe_compact(false);
         }
-        sync_and_maybe_compact(true);
-        // ---- deliver this CTA's list; the CTA that delivers the last one finishes the query
-        {
-            const uint32_t cnt = s_count[0];
-            uint64_t* out = P.lists + ((size_t)slot * gridDim.x + blockIdx.x) * p.k;
-            for (uint32_t i = ctid; i < p.k; i += nct) out[i] = (i < cnt) ? s_cand[i] : 0ull;
-        }
-        __threadfence();
+        while (next_boundary < my_tiles) { sync_and_maybe_compact(); next_boundary += epoch_tiles; }
+        // hand the candidates to the helper and move straight on to the next query's rows
         named_bar_sync(1, nct);
-        if (ctid == 0) {
-            const uint32_t old = atomicAdd(&P.ctrl->done[slot], 1u);
-            sts_volatile(&s_ctl[4], old == gridDim.x - 1 ? 1u : 0u);
-        }
-        named_bar_sync(1, nct);
-        if (lds_volatile(&s_ctl[4])) {
-            __threadfence();
-            // queries are finalised in order (the exchange's two-parity slots and the host's completion word rely on it)
-            if (ctid == 0) {
-                uint32_t spins = 0;
-                const uint64_t t0 = global_ns();
-                while ((int32_t)(ld_acquire_gpu(&P.ctrl->completed) + 1 - cur) < 0) { CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
-            }
-            named_bar_sync(1, nct);
-            const uint32_t cwarp = warp;
-            const uint32_t n_lists = gridDim.x, total = n_lists * p.k;
-            uint64_t* staged = s_merge;                          // [n_lists * k]
-            uint64_t* lvl = s_merge + total;                     // [8][k]
-            uint64_t* best = lvl + 8 * p.k;                      // [k]
-            const uint64_t* src = P.lists + (size_t)slot * gridDim.x * p.k;
-            for (uint32_t i = ctid; i < total; i += nct) staged[i] = __ldcg(src + i);
-            named_bar_sync(1, nct);
-            const uint32_t nw = (n_lists + 31) / 32;
-            if (cwarp < nw) warp_tournament_topk(staged + (size_t)cwarp * 32 * p.k, min(32u, n_lists - cwarp * 32), p.k, p.k, p.k, lvl + (size_t)cwarp * p.k, lane);
-            named_bar_sync(1, nct);
-            if (cwarp == 0) warp_tournament_topk(lvl, nw, p.k, p.k, p.k, best, lane);
-            named_bar_sync(1, nct);
-            const ServeDesc* dd = &P.ctrl->ddesc[slot];
-            if (P.world > 1) {
-                // the peer exchange of exchange.cuh, executed by this CTA: push, publish, wait, gather, merge
-                const uint32_t xseq = __ldcg(&dd->xseq), parity = xseq & 1u;
-                for (uint32_t i = ctid; i < P.world * p.k; i += nct) {
-                    const uint32_t r = i / p.k, j = i - r * p.k;
-                    xchg_slot(P.peer[r], parity, P.rank, 0)[j] = best[j];
-                }
-                __threadfence_system();
-                named_bar_sync(1, nct);
-                if (ctid < P.world) st_release_sys(&xchg_flags(P.peer[ctid])[P.rank * kXchgMaxQ], xseq);
-                if (ctid < P.world) {
-                    const uint32_t* f = &xchg_flags(P.peer[P.rank])[ctid * kXchgMaxQ];
-                    const uint64_t t0 = global_ns();
-                    uint32_t spins = 0;
-                    while ((int32_t)(ld_acquire_sys(f) - xseq) < 0) {
-                        if ((++spins & 1023u) == 0 && global_ns() - t0 > P.xchg_timeout_ns) { atomicExch_system(const_cast<uint32_t*>(&P.host->error), 1u + ctid); break; }
-                    }
-                }
-                named_bar_sync(1, nct);
-                for (uint32_t i = ctid; i < P.world * p.k; i += nct) {
-                    const uint32_t r = i / p.k, j = i - r * p.k;
-                    staged[i] = __ldcg(xchg_slot(P.peer[P.rank], parity, r, 0) + j);
-                }
-                named_bar_sync(1, nct);
-                if (cwarp == 0) warp_tournament_topk(staged, P.world, p.k, p.k, p.k, best, lane);
-                named_bar_sync(1, nct);
-            }
-            uint64_t* o_rows = reinterpret_cast<uint64_t*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->out_rows)));
-            float* o_scores = reinterpret_cast<float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->out_scores)));
-            uint32_t* o_counts = reinterpret_cast<uint32_t*>(__ldcg(reinterpret_cast<const unsigned long long*>(&dd->out_counts)));
-            uint32_t cnt = 0;
-            for (uint32_t i = ctid; i < p.k; i += nct) {
-                const uint64_t key = best[i];
-                const bool valid = key != 0ull;
-                if (o_rows) o_rows[i] = valid ? (uint64_t)key_row(key) : ~0ull;
-                if (o_scores) o_scores[i] = valid ? key_score(key, ascending) : 0.0f;
-                cnt += valid;
-            }
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0 && cnt) atomicAdd(&s_ctl[5], cnt);
-            __threadfence_system();
-            named_bar_sync(1, nct);
-            if (ctid == 0) {
-                if (o_counts) *o_counts = lds_volatile(&s_ctl[5]);
-                sts_volatile(&s_ctl[5], 0u);
-                P.ctrl->done[slot] = 0;
-                __threadfence_system();
-                st_release_gpu(&P.ctrl->completed, cur);
-                st_release_sys(const_cast<uint32_t*>(&P.host->completed), cur);
-            }
-            named_bar_sync(1, nct);
-        }
-        ++cur;
+        if (ctid == 0) { mbar_arrive(&cand_full[b]); mbar_arrive(&q_free[b]); }
     }
-    // ---- leaving: tell the producer, then wait for every copy it has issued (shared memory must outlive the TMA writes)
-    if (ctid == 0) sts_volatile(&s_ctl[1], 1u);
+    // ---- leaving: wait for every copy the producer has issued (shared memory must outlive the TMA writes)
     {
         uint32_t spins = 0;
-        const uint64_t t0 = global_ns();
-        while (lds_volatile(&s_ctl[2]) == 0u) { CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
+        uint64_t t0 = 0;
+        while (lds_volatile(&s_ctl[kCtlProdDone]) == 0u) { CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }
         __threadfence_block();
-        const uint64_t issued = lds_volatile(&s_ctl[3]);         // stage counts stay far below 2^32 within one launch (life_ns)
+        const uint64_t issued = lds_volatile(&s_ctl[kCtlIssued]);    // stage counts stay far below 2^32 within one launch (life_ns)
         for (; n < issued; n += ngroups) {
             const uint32_t s = (uint32_t)(n % p.stages), par = (uint32_t)((n / p.stages) & 1);
             while (!mbar_try_wait(&full_bar[s], par)) { CGV_SERVE_SPIN_GUARD(spins, t0, P.abort_ns) }

@@ -155,6 +155,32 @@ int cgvec_stream_submit(cgvec_stream* s, const float* queries /* nq x dim, host 
 int cgvec_stream_flush(cgvec_stream* s, uint64_t* out_rows, float* out_scores, uint32_t* out_counts, uint32_t* out_nq);
 int cgvec_stream_close(cgvec_stream* s);
 
+/* ---- resident batch-1 sessions ------------------------------------------------------------------
+ * The reference serves one search_similar call per query (VectorStore::search_similar, codegraph-core/src/traits.rs:11-16;
+ * SemanticSearch::search_by_embedding, codegraph-vector/src/search.rs:91-144).  A session keeps the exact-order scan kernel
+ * RESIDENT between those calls: a submit is a 64-byte descriptor and a doorbell word in pinned memory, a completion is a word
+ * the host spins on — no kernel launch, copy node or stream synchronisation per query.  The kernel is started on demand, leaves
+ * by itself after `idle_us` without work (it owns every SM while resident) and is restarted transparently.  Results are
+ * bit-identical to cgvec_search (same kernels' arithmetic and keys).  1 <= k <= 64; cosine / dot / L2; single-device indexes
+ * and the ranks of a sharded index (every rank opens a session and submits the same queries in the same order).
+ * cgvec_serve_search: host buffers, blocking.  cgvec_serve_submit + cgvec_serve_wait: pipelined; with device_io the query
+ * (dim rounded up to 4 floats) and the result buffers are device memory.  At most 6 tickets may be outstanding.
+ * The write side of the index refuses to run while a session is open. */
+typedef struct cgvec_server cgvec_server;
+int cgvec_serve_open(cgvec_index* idx, uint32_t k, cgvec_metric metric, cgvec_server** out);
+int cgvec_serve_search(cgvec_server* s, const float* query, uint64_t* out_rows, uint8_t (*out_ids)[16], float* out_scores, uint32_t* out_count);
+int cgvec_serve_submit(cgvec_server* s, const float* query, int device_io, uint64_t* out_rows, float* out_scores, uint32_t* out_count,
+                       uint32_t* out_ticket);
+int cgvec_serve_wait(cgvec_server* s, uint32_t ticket);
+int cgvec_serve_pause(cgvec_server* s);                          /* ask the resident kernel to leave now; the next submit restarts it */
+/* CUDA-event bracket on the session's launch stream: start pauses the session and records; the kernel launch of the next submit,
+ * every query and the kernel's exit lie inside; stop drains, makes the kernel leave, records and returns the elapsed ms. */
+int cgvec_serve_timer_start(cgvec_server* s);
+int cgvec_serve_timer_stop(cgvec_server* s, float* out_ms);
+int cgvec_serve_stats(const cgvec_server* s, uint64_t* out_kernel_launches, uint64_t* out_queries_served);
+int cgvec_serve_set(cgvec_server* s, const char* key, int64_t value);   /* idle_us, life_ms, abort_ms, wait_ms, chunk_tiles */
+int cgvec_serve_close(cgvec_server* s);
+
 /* VectorStore::get_embedding: copies the row (widened to f32) into out_row[dim]; CGVEC_ERR_NOT_FOUND -> None. */
 int cgvec_get(const cgvec_index* idx, const uint8_t id[16], float* out_row);
 int cgvec_get_row(const cgvec_index* idx, uint64_t local_row, float* out_row);

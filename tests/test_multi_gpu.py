@@ -321,3 +321,76 @@ def test_uneven_shards_take_the_same_path_on_every_rank(oracle):
     qsets = [rng.standard_normal((64, d)).astype(np.float32)]
     st = _run_general(oracle, rows, qsets, k, [0, 40_000, 70_000], "f16", "auto", reps=2)
     assert len({v[0] > 0 for v in st.values()}) == 1, "ranks disagreed on the kernel family"
+
+
+def _worker_session(rank, world, uid_q, rows, qs, k, out, skew_rank):
+    """Every rank opens a resident session on its shard and submits the same queries in the same order; the CTA that finishes a
+    query on each rank runs the NVLink peer exchange inside the resident kernel."""
+    sys.path.insert(0, ROOT)
+    import time
+    import __graft_entry__ as ge
+    cg = ge.load_package()
+    import torch
+    torch.cuda.set_device(rank)
+    if rank == 0:
+        uid = cg.nccl_unique_id()
+        for _ in range(world - 1):
+            uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    b, e = cg.shard_range(len(rows), world, rank)
+    ix = cg.Index(rows.shape[1], cg.F32, device=rank, rank=rank, world=world, nccl_unique_id=uid, row_offset=b)
+    ix.add(rows[b:e])
+    r0, s0, _ = ix.search(qs[0], k)                              # launch-per-query path first (shares the exchange buffers and counter)
+    sess = cg.ServeSession(ix, k, idle_us=300)
+    res = []
+    rng = np.random.default_rng(rank)
+    for i, q in enumerate(qs):
+        if rank == skew_rank and i % 3 == 0:
+            time.sleep(float(rng.uniform(0.0, 0.003)))           # one rank dawdles: the others' finishing CTAs wait in the exchange
+        r, s, c = sess.search(q)
+        res.append((r.tolist(), s.tobytes(), int(c)))
+    # pipelined device-resident submissions
+    dq = torch.from_numpy(qs).cuda()
+    d_rows = torch.full((len(qs), k), -1, dtype=torch.int64, device="cuda"); d_scores = torch.zeros((len(qs), k), dtype=torch.float32, device="cuda")
+    d_counts = torch.zeros((len(qs),), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    t = 0
+    for i in range(len(qs)):
+        t = sess.submit_device(dq[i].data_ptr(), d_rows[i].data_ptr(), d_scores[i].data_ptr(), d_counts[i].data_ptr())
+    sess.wait(t)
+    st = sess.stats()
+    sess.close()
+    r1, s1, _ = ix.search(qs[1], k)                              # and the launch path again after the session
+    out[rank] = (res, d_rows.cpu().numpy().tolist(), d_scores.cpu().numpy().tobytes(), r0[0].tolist(), r1[0].tolist(), st["launches"])
+    ix.close()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_resident_sessions_on_a_sharded_index(oracle):
+    import torch.multiprocessing as mp
+    world = min(_ngpus(), 4)
+    rng = np.random.default_rng(91)
+    n, d, k, nq = 30_000 * world + 17, 128, 10, 24
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[n - 5] = rows[11]                                       # a tie across shards: the lower global row wins
+    qs = rng.standard_normal((nq, d)).astype(np.float32)
+    qs[2] = rows[11]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict(); uid_q = ctx.Queue()
+        procs = [ctx.Process(target=_worker_session, args=(r, world, uid_q, rows, qs, k, out, world - 1)) for r in range(world)]
+        [p.start() for p in procs]
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0, "a rank failed or hung"
+        want = [oracle.parallel_top_k_search(q, rows, k) for q in qs]
+        for r in range(world):
+            res, drows, dscores, r0, r1, launches = out[r]
+            ds = np.frombuffer(dscores, np.float32).reshape(nq, k)
+            assert launches >= 1
+            assert r0 == want[0][0].tolist() and r1 == want[1][0].tolist()
+            for i in range(nq):
+                wi, ws = want[i]
+                assert res[i][0] == wi.tolist() and res[i][1] == ws.tobytes() and res[i][2] == k, (r, i)
+                assert drows[i] == wi.tolist() and ds[i].tobytes() == ws.tobytes(), (r, i)
