@@ -518,9 +518,21 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- pre-warm: at least 200 ms of the same steps whatever --warmup says (clocks, L2 / TLB state, NCCL channels), so that
     #      a 20-step driver run measures the steady state and not the first two milliseconds after idle
-    t_pre = time.perf_counter()
+    #      The number of rounds is agreed over the ranks (max of one timed round): every rank must issue the SAME number of
+    #      searches, each of them carries one exchange step (a per-rank wall-clock loop ran different counts on different ranks
+    #      and the surplus steps timed out waiting for peers that had moved on — found at 8 GPUs in r02).
     with torch.cuda.stream(stream):
-        while time.perf_counter() - t_pre < 0.25:
+        for i in range(args.warmup):                             # first round: module load, attribute calls, scratch allocation
+            step_device(i)
+        torch.cuda.synchronize()
+        env.barrier()
+        t_pre = time.perf_counter()
+        for i in range(args.warmup):
+            step_device(i)
+        torch.cuda.synchronize()
+        round_s = env.max_over_ranks(time.perf_counter() - t_pre)
+        rounds = int(min(500, max(1, np.ceil(0.25 / max(round_s, 1e-5)))))
+        for _ in range(rounds):
             for i in range(args.warmup):
                 step_device(i)
             torch.cuda.synchronize()
