@@ -5,17 +5,19 @@
 // second launch for merge + exchange at the tail).  Here the CTAs stay resident across queries:
 //
 //   * the host submits a query by writing a descriptor into a pinned, device-mapped ring and bumping a doorbell word; the
-//     poller warp of CTA 0 reads it over PCIe, stages host-resident queries into device memory and publishes the sequence
-//     number to the other CTAs (one L2 word);
-//   * the PRODUCER warp of every CTA is query-agnostic: it claims chunks of row tiles from one monotonic ticket counter
-//     (ticket -> query = ticket / chunks_per_query, so the matrix is simply streamed round and round) and keeps its TMA
-//     ring full — the first tiles of the next query are already in shared memory while the consumers finish the current
-//     one, and a CTA that falls behind (it merged the previous query) just claims fewer chunks;
-//   * the 8 CONSUMER warps score rows in the reference's exact order with the very same code as K1 (score_row_octet),
-//     keep the CTA's best k, and at the end-of-query marker write their list; the CTA that delivers the LAST list of a
-//     query merges all of them, runs the NVLink peer exchange on a sharded index (same protocol and buffers as
-//     exchange.cuh), decodes the result straight into the submitter's buffers (pinned host memory for host I/O) and
-//     publishes the completion word the host spins on.
+//     POLLER warp of CTA 0 reads it over PCIe, stages host-resident queries into device memory and publishes the sequence
+//     number on one 128-byte line per CTA;
+//   * the PRODUCER warp of every CTA is query-agnostic: stage n always carries tile blockIdx + (n mod tiles) * grid (K1's
+//     static assignment), so the shard is streamed round and round through the TMA ring — the first tiles of the next
+//     query are already in shared memory while the consumers finish the current one;
+//   * the 8 CONSUMER warps score rows in the reference's exact order with the very same code as K1 (score_row_octet) and
+//     derive query and tile of a stage from its number alone; per query they only flip between two query buffers and two
+//     candidate buffers;
+//   * the HELPER warp prefetches the next query (and its squared norm, in the reference's order) into the other buffer;
+//     at the end of a query it sorts the CTA's candidates, writes the CTA's list and counts it in; on the CTA that
+//     delivered the LAST list of the query it merges all lists, runs the NVLink peer exchange on a sharded index (same
+//     protocol and buffers as exchange.cuh), decodes the result straight into the submitter's buffers (pinned host memory
+//     for host I/O) and publishes the completion word the host spins on.
 //
 // No launch, no memcpy node and no stream synchronisation per query.  The kernel leaves on its own after `idle_ns` without a
 // doorbell (a resident grid owns every SM) and the host transparently relaunches it; every spin is bounded by a watchdog
@@ -33,7 +35,6 @@ constexpr int kServeThreads = 32 * (kServeConsumerWarps + 3);      // + producer
 constexpr uint32_t kServeSlots = 8;                                // descriptor ring depth = most queries in flight
 constexpr uint32_t kServeMaxK = 64;
 constexpr uint32_t kServeMaxGrid = 192;                            // CTAs of a session (one per SM)
-constexpr uint32_t kServeMarkEnd = 0xffffffffu, kServeMarkEmpty = 0xfffffffeu;
 
 struct ServeDesc {                   // one submitted query; written by the host BEFORE the doorbell is bumped
     uint64_t q_ptr;                  // device-accessible address of the query (qstride f32); pinned host memory when q_on_host
@@ -56,12 +57,11 @@ struct ServeHostBlock {              // pinned + mapped into the device address 
 };
 
 struct ServeCtrl {                   // device memory, reset by the host before every launch
-    unsigned long long ticket;       // next chunk of row tiles
+    unsigned long long reserved0;
     uint32_t go;                     // highest sequence number published to the CTAs
     uint32_t exit_seq;               // 0 while running, else the first sequence number this launch does not serve
     uint32_t completed;              // highest sequence number finalised
-    uint32_t pass_done;              // producers that have finished issuing a pass over the shard (lockstep option), summed over passes
-    uint32_t pad[2];
+    uint32_t pad[3];
     uint32_t done[kServeSlots];      // lists delivered, per sequence slot
     ServeDesc ddesc[kServeSlots];    // device copy of the descriptors (q_ptr already pointing into device memory)
     // One 128-byte line per CTA: [0] = go, [1] = exit_seq as seen by THAT CTA's helper warp.  148 helpers polling one word
@@ -72,11 +72,9 @@ struct ServeCtrl {                   // device memory, reset by the host before 
 struct ServeParams {
     ScanParams sp;                   // rows, norms, n_rows, d, ld, row_words, tile_rows, stages, active_groups, k, cand_cap, row mapping
     uint32_t epoch_rounds;           // stages per consumer group between threshold syncs
-    uint32_t chunk_tiles;            // row tiles per ticket (multiple of the group count)
     uint32_t start_seq;              // first sequence number this launch serves
-    uint32_t off_tile, off_ctl, off_merge, smem_total;   // extra shared-memory regions behind K1's layout
+    uint32_t off_ctl, off_merge, smem_total;   // extra shared-memory regions behind K1's layout: barriers + control words, merge staging
     uint32_t merge_lists;            // per-CTA lists the finishing CTA stages at once (multiple of 32, <= 256)
-    uint32_t lockstep;               // (unused)
     uint32_t contig;                 // 1: every CTA streams one contiguous run of row tiles instead of K1's interleaved ones
     ServeCtrl* ctrl;
     ServeHostBlock* host;            // device pointer of the mapped block

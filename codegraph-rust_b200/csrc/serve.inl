@@ -37,7 +37,7 @@ namespace {
 
 __global__ void serve_reset_kernel(ServeCtrl* c, uint32_t last_done) {
     if (threadIdx.x == 0) {
-        c->ticket = 0ull; c->go = last_done; c->exit_seq = 0; c->completed = last_done; c->pass_done = 0;
+        c->reserved0 = 0ull; c->go = last_done; c->exit_seq = 0; c->completed = last_done;
         for (uint32_t i = 0; i < kServeSlots; ++i) c->done[i] = 0;
     }
     for (uint32_t i = threadIdx.x; i < kServeMaxGrid; i += blockDim.x) { c->cta_line[i][0] = last_done; c->cta_line[i][1] = 0; }
@@ -138,11 +138,8 @@ int serve_open_impl(Index* ix, uint32_t k, int metric, cgvec_server** out) {
     P.sp.d = ix->dim; P.sp.ld = ix->ld; P.sp.row_words = g.row_words; P.sp.tile_rows = g.tile_rows; P.sp.stages = g.stages;
     P.sp.active_groups = g.groups; P.sp.k = k; P.sp.cand_cap = g.cand_cap; P.sp.sync_interval = g.sync_interval; P.sp.use_l2_hint = ix->opt_l2_hint;
     P.epoch_rounds = g.sync_interval / g.groups;
-    const uint64_t tiles = (ix->n + g.tile_rows - 1) / g.tile_rows;
-    P.chunk_tiles = g.groups * (tiles / g.grid >= 64 ? 2u : 1u);
     const ScanSmemLayout L = scan_smem_layout(g.row_words, g.tile_rows, g.stages, ix->dim, 2, g.cand_cap);
-    P.off_tile = (L.total + 15) & ~15u;
-    P.off_ctl = P.off_tile + ((g.stages * 4 + 15) & ~15u);
+    P.off_ctl = (L.total + 15) & ~15u;
     P.off_merge = P.off_ctl + 128;                               // 8 mbarriers + control words + the two query norms
     P.merge_lists = merge_lists;
     P.smem_total = P.off_merge + (uint32_t)(((size_t)merge_lists * k + 9 * k) * 8);
@@ -350,12 +347,9 @@ CGVEC_EXPORT int cgvec_serve_set(cgvec_server* s, const char* key, int64_t value
     else if (k == "abort_ms") { s->abort_ms = (int)value; s->P.abort_ns = (uint64_t)value * 1000000ull; }
     else if (k == "wait_ms") s->wait_ms = (int)value;
     else if (k == "l2_hint") s->P.sp.use_l2_hint = (uint32_t)value;
-    else if (k == "lockstep") s->P.lockstep = (uint32_t)value;
     else if (k == "contig") s->P.contig = (uint32_t)value;
     else if (k == "max_inflight") s->max_inflight = value < 1 ? 1 : value > (int64_t)kServeSlots - 2 ? (int)kServeSlots - 2 : (int)value;
-    else if (k == "chunk_tiles") s->P.chunk_tiles = (uint32_t)value / s->P.sp.active_groups * s->P.sp.active_groups;
     else return fail(CGVEC_ERR_BAD_ARG, "unknown session option '%s'", key);
-    if (s->P.chunk_tiles == 0) s->P.chunk_tiles = s->P.sp.active_groups;
     return CGVEC_OK;
 }
 CGVEC_EXPORT int cgvec_serve_close(cgvec_server* s) {

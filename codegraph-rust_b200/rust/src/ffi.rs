@@ -28,6 +28,26 @@ pub struct cgvec_search_opts {
     pub device_io: c_int,
 }
 
+#[repr(C)]
+pub struct cgvec_server {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    // resident batch-1 sessions (include/cgvec.h, "resident batch-1 sessions"): the scan kernel stays on the GPU between calls
+    pub fn cgvec_serve_open(idx: *mut cgvec_index, k: u32, metric: c_int, out: *mut *mut cgvec_server) -> c_int;
+    pub fn cgvec_serve_search(
+        s: *mut cgvec_server,
+        query: *const f32,
+        out_rows: *mut u64,
+        out_ids: *mut [u8; 16],
+        out_scores: *mut f32,
+        out_count: *mut u32,
+    ) -> c_int;
+    pub fn cgvec_serve_pause(s: *mut cgvec_server) -> c_int;
+    pub fn cgvec_serve_close(s: *mut cgvec_server) -> c_int;
+}
+
 extern "C" {
     pub fn cgvec_create(dim: u32, storage: c_int, device_ids: *const c_int, n_devices: c_int, out: *mut *mut cgvec_index) -> c_int;
     pub fn cgvec_create_from_env(dim: u32, storage: c_int, enable_gpu: c_int, out: *mut *mut cgvec_index) -> c_int;

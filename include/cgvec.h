@@ -178,7 +178,7 @@ int cgvec_serve_pause(cgvec_server* s);                          /* ask the resi
 int cgvec_serve_timer_start(cgvec_server* s);
 int cgvec_serve_timer_stop(cgvec_server* s, float* out_ms);
 int cgvec_serve_stats(const cgvec_server* s, uint64_t* out_kernel_launches, uint64_t* out_queries_served);
-int cgvec_serve_set(cgvec_server* s, const char* key, int64_t value);   /* idle_us, life_ms, abort_ms, wait_ms, chunk_tiles */
+int cgvec_serve_set(cgvec_server* s, const char* key, int64_t value);   /* idle_us, life_ms, abort_ms, wait_ms, max_inflight, l2_hint, contig */
 int cgvec_serve_close(cgvec_server* s);
 
 /* VectorStore::get_embedding: copies the row (widened to f32) into out_row[dim]; CGVEC_ERR_NOT_FOUND -> None. */

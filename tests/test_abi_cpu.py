@@ -80,6 +80,18 @@ def test_argument_validation_never_aborts(cg):
     assert lib.cgvec_len(None) == 0
     assert lib.cgvec_create_rank(8, 0, 0, 2, 2, None, 0, C.byref(h)) == cg.ERR_BAD_ARG
     assert b"rank" in lib.cgvec_last_error()
+    # resident sessions and streams: NULL handles are errors (or no-ops for close), never a crash
+    t = C.c_uint32(); ms = C.c_float()
+    assert lib.cgvec_serve_open(None, 10, 0, C.byref(h)) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_search(None, None, None, None, None, None) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_submit(None, None, 0, None, None, None, C.byref(t)) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_wait(None, 1) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_pause(None) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_timer_start(None) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_timer_stop(None, C.byref(ms)) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_set(None, b"idle_us", 1) == cg.ERR_BAD_ARG
+    assert lib.cgvec_serve_close(None) == 0
+    assert lib.cgvec_stream_close(None) == 0
 
 
 def test_shard_range_covers_and_partitions(cg):

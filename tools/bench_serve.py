@@ -43,7 +43,7 @@ def main():
         rec["launch_device_us"] = round(e0.elapsed_time(e1) / args.steps * 1e3, 2)
         for chunk in args.chunks:
             s = cg.ServeSession(ix, args.k)
-            if chunk: s.set("contig", chunk - 1)            # --chunks 1 2 -> interleaved / contiguous tile runs per CTA
+            if chunk: s.set("contig", chunk - 1)            # --chunks 1 2 -> interleaved / contiguous tile runs per CTA (A/B knob)
             qrows = [np.ascontiguousarray(qs[i]) for i in range(64)]
             for i in range(20): s.search_raw(qrows[i % 64])
             t0 = time.perf_counter()
