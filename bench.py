@@ -488,6 +488,11 @@ def run_batched(env, name):
                     "parity_ok": bool(all(r["parity_ok"] for r in out["runs"])), "tc_fallbacks": sum(r["tc_fallbacks"] for r in out["runs"]),
                     "roofline": first["roofline"]})
     finally:
+        try:
+            if "qstream" in locals() and qstream is not None:   # an exception between open and close: the index refuses to go while a stream is open
+                qstream.close()
+        except Exception:
+            pass
         ix.close()
         torch.cuda.empty_cache()
     return out
@@ -626,6 +631,10 @@ def run_b200(args, rank, world, local_rank):
                    "timing": "device_resident: CUDA events on the session's launch stream around kernel launch + K individually submitted queries + kernel exit, max over ranks; e2e: host wall clock"}
     except Exception as e:
         session = {"error": repr(e)[:300]}
+        try:
+            sess.close()                                     # an open session would keep the index (and every SM) busy
+        except Exception:
+            pass
     env.barrier()
 
     # ---- concurrent batch-1 callers (multi_vector_search's shape, search.rs:347-361): 16 host threads, group commit on / off ----

@@ -320,7 +320,9 @@ class Index:
     # -- lifecycle
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            load_library().cgvec_destroy(self._h)
+            rc = load_library().cgvec_destroy(self._h)
+            if rc:                                             # sessions still open: the index stays alive
+                _check(rc)
             self._h = C.c_void_p()
 
     def __del__(self):

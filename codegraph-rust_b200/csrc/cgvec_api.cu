@@ -515,6 +515,8 @@ CGVEC_EXPORT int cgvec_nccl_unique_id(void* out_128_bytes) {
 
 CGVEC_EXPORT int cgvec_destroy(cgvec_index* ix) {
     if (!ix) return CGVEC_OK;
+    if (ix->open_streams.load() > 0)                             // they hold pointers into this index (and maybe a resident kernel)
+        return fail(CGVEC_ERR_UNSUPPORTED, "close the index's cgvec_stream / cgvec_serve sessions before destroying it");
     if (!ix->parts.empty()) { multi_destroy(ix); return CGVEC_OK; }
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();

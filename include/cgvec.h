@@ -108,7 +108,7 @@ int cgvec_create_rank(uint32_t dim, cgvec_dtype storage, int device, int rank, i
                       const void* nccl_unique_id, uint64_t row_offset, cgvec_index** out);
 int cgvec_nccl_unique_id(void* out_128_bytes);
 
-int cgvec_destroy(cgvec_index* idx);
+int cgvec_destroy(cgvec_index* idx);   /* CGVEC_ERR_UNSUPPORTED while cgvec_stream / cgvec_serve sessions of the index are open */
 
 /* ---- write side: VectorStore::store_embeddings ----------------------------------------------- */
 

@@ -67,6 +67,10 @@ def test_session_ids_zero_norm_rows_and_small_k(cg, oracle):
     q = rows[123]
     r, sc, c, gids = s.search(q, want_ids=True)
     assert c == 1 and int(r[0]) == 123 and gids[0].tobytes() == ids[123].bytes
+    with pytest.raises(cg.CgvecError):
+        ix.close()                                               # an open session keeps the index alive
+    with pytest.raises(cg.CgvecError):
+        ix.add(rows[:1])                                         # and the write side out
     s.close()
     s = cg.ServeSession(ix, 64)
     for q in rng.standard_normal((3, d)).astype(np.float32):
