@@ -598,6 +598,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- resident session (cgvec_serve_*): the same batch-1 queries served by a kernel that stays on the GPU ----
     session = None
     try:
+        if args.no_extras:
+            raise RuntimeError("skipped (--no-extras)")
         sess = cg.ServeSession(ix, k)
         for i in range(min(args.warmup, 5)):
             sess.search_raw(q_rows[i][0])
@@ -639,7 +641,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- concurrent batch-1 callers (multi_vector_search's shape, search.rs:347-361): 16 host threads, group commit on / off ----
     concurrent = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         try:
             import threading
             nthreads, per = 16, max(8, min(64, args.steps // 8))
@@ -801,6 +803,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--configs", default="c3,c4,c5", help="comma-separated batched configs to add to the line (c3,c4,c5) or 'none'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the resident-session and concurrent-caller records (profiler runs: a resident kernel must not be serialised by ncu)")
     ap.add_argument("--opt", action="append", type=lambda s: (s.split("=")[0], int(s.split("=")[1])),
                     help="library tuning knob key=value (repeatable)")
     args = ap.parse_args()
