@@ -36,7 +36,7 @@ EXPORTS = [
     "cgvec_create", "cgvec_create_from_env", "cgvec_create_rank", "cgvec_nccl_unique_id", "cgvec_destroy", "cgvec_reserve", "cgvec_add",
     "cgvec_add_f16", "cgvec_normalize_rows", "cgvec_fill_synthetic", "cgvec_len", "cgvec_dim", "cgvec_search",
     "cgvec_search_ex", "cgvec_get", "cgvec_get_row", "cgvec_get_rows", "cgvec_row_of_id", "cgvec_rescore", "cgvec_distances_first",
-    "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_multi_locate", "cgvec_multi_local_count", "cgvec_merge_topk_host", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
+    "cgvec_quantize_i8", "cgvec_get_codes_i8", "cgvec_search_i8", "cgvec_save_flat", "cgvec_load_flat", "cgvec_shard_range", "cgvec_multi_locate", "cgvec_multi_local_count", "cgvec_merge_topk_host", "cgvec_path_cost_model", "cgvec_prefetch_k_basic", "cgvec_prefetch_k_filtered",
     "cgvec_normalize_scores", "cgvec_get_stats", "cgvec_set_option", "cgvec_get_trace", "cgvec_last_error", "cgvec_version",
     "cgvec_stream_open", "cgvec_stream_submit", "cgvec_stream_flush", "cgvec_stream_close",
     "cgvec_serve_open", "cgvec_serve_submit", "cgvec_serve_wait", "cgvec_serve_search", "cgvec_serve_pause", "cgvec_serve_stats",
@@ -159,6 +159,15 @@ def _ids_to_bytes(ids) -> Optional[np.ndarray]:
         assert len(b) == 16
         out[i] = np.frombuffer(b, np.uint8)
     return out
+
+
+def path_cost_model(dtype: int, dim: int, rows: int, nq: int, tensor_batch_limit: int = 128):
+    """(exact_ms, tensor_ms) of AUTO's cost model for one call with nq queries."""
+    L = load_library()
+    L.cgvec_path_cost_model.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    a, b = C.c_double(), C.c_double()
+    _check(L.cgvec_path_cost_model(dtype, dim, rows, nq, tensor_batch_limit, C.byref(a), C.byref(b)))
+    return float(a.value), float(b.value)
 
 
 def version() -> str:

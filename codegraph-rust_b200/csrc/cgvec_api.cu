@@ -1452,6 +1452,14 @@ CGVEC_EXPORT int cgvec_merge_topk_host(const uint64_t* rows, const float* scores
     return CGVEC_OK;
 }
 
+// AUTO's cost model as a pure function (milliseconds per call on the exact-order kernel and on the tensor path).
+CGVEC_EXPORT int cgvec_path_cost_model(cgvec_dtype storage, uint32_t dim, uint64_t rows, uint32_t nq, uint32_t tensor_batch_limit,
+                                       double* out_exact_ms, double* out_tensor_ms) {
+    if (!out_exact_ms || !out_tensor_ms || dim == 0 || nq == 0) return fail(CGVEC_ERR_BAD_ARG, "bad argument");
+    tensor_cost_model(storage == CGVEC_F32, dim, rows, nq, tensor_batch_limit, out_exact_ms, out_tensor_ms);
+    return CGVEC_OK;
+}
+
 CGVEC_EXPORT uint64_t cgvec_prefetch_k_basic(uint64_t limit) {       // search.rs:113
     uint64_t a = limit > UINT64_MAX / 3 ? UINT64_MAX : limit * 3, b = limit + 10;
     return a > b ? a : b;

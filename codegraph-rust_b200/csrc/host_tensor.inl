@@ -291,16 +291,21 @@ int tensor_batch(Index* ix, SearchCtx* c, const float* d_q, uint32_t qstride, ui
 //                                   wavefronts per element, not by bytes); 2 queries 1.12 u, 4 queries 1.63 u per launch
 //   tensor pass (<= n_max queries) 0.15 + rows*dim*esize / 6.6e9 + MMA time (matters beyond ~64 queries only)
 // Batch-1 always stays on the exact-order kernel (fully asynchronous, fused peer exchange, resident server).
+// the two estimates in milliseconds (pure function of the shape: exported as cgvec_path_cost_model for the CPU test tier)
+void tensor_cost_model(bool f32, uint32_t dim, uint64_t rows, uint32_t nq, uint32_t n_max, double* t_exact, double* t_tensor) {
+    const double elems = (double)rows * dim;
+    const double u = 0.03 + elems * 4.0 / 7.0e9;
+    const uint32_t n4 = nq / 4, r = nq % 4;
+    *t_exact = n4 * 1.63 * u + (r == 3 ? 2.12 * u : r == 2 ? 1.12 * u : r == 1 ? u : 0.0);
+    const uint32_t passes = n_max ? (nq + n_max - 1) / n_max : 1;
+    const double mma_rate = f32 ? 6.0e11 : 1.2e12;                               // sustained flop per ms under the power cap
+    *t_tensor = passes * (0.15 + elems * (f32 ? 4 : 2) / 6.6e9) + 2.0 * elems * nq / mma_rate;
+}
 bool tensor_auto_rule(const Index* ix, uint64_t rows, uint32_t nq, uint32_t k, uint32_t n_max) {
     if (rows < 4 * kTcCap || k > kTcCap / 16 || nq < 2 || n_max == 0) return false;
     if (ix->opt_tc_min_nq > 0) return nq >= (ix->dtype == CGVEC_F32 ? (uint32_t)ix->opt_tc_min_nq * 2 : (uint32_t)ix->opt_tc_min_nq);
-    const double elems = (double)rows * ix->dim;
-    const double u = 0.03 + elems * 4.0 / 7.0e9;
-    const uint32_t n4 = nq / 4, r = nq % 4;
-    const double t_exact = n4 * 1.63 * u + (r == 3 ? 2.12 * u : r == 2 ? 1.12 * u : r == 1 ? u : 0.0);
-    const uint32_t passes = (nq + n_max - 1) / n_max;
-    const double mma_rate = ix->dtype == CGVEC_F32 ? 6.0e11 : 1.2e12;            // sustained flop per ms under the power cap
-    const double t_tensor = passes * (0.15 + elems * ix->esize / 6.6e9) + 2.0 * elems * nq / mma_rate;
+    double t_exact = 0.0, t_tensor = 0.0;
+    tensor_cost_model(ix->dtype == CGVEC_F32, ix->dim, rows, nq, n_max, &t_exact, &t_tensor);
     return t_tensor < t_exact;
 }
 bool tensor_auto_ok(const Index* ix, int metric, uint32_t nq, uint32_t k) {

@@ -226,6 +226,10 @@ uint64_t cgvec_multi_local_count(uint32_t n_devices, uint32_t shard, uint64_t n_
 int cgvec_merge_topk_host(const uint64_t* rows, const float* scores, const uint32_t* counts, uint32_t parts,
                           uint32_t k, int ascending, uint64_t* out_rows, float* out_scores, uint32_t* out_count);
 /* search.rs:113 and :276 over-fetch sizes; search.rs:574-592 min-max normalisation. */
+/* CGVEC_PATH_AUTO's cost model (DESIGN.md §5 "AUTO"): estimated milliseconds of one call with nq queries on the exact-order kernel
+ * and on the tensor path (tensor_batch_limit = queries one tensor pass takes: 128, or 256 with the paired kernel).  Pure function. */
+int cgvec_path_cost_model(cgvec_dtype storage, uint32_t dim, uint64_t rows, uint32_t nq, uint32_t tensor_batch_limit,
+                          double* out_exact_ms, double* out_tensor_ms);
 uint64_t cgvec_prefetch_k_basic(uint64_t limit);
 uint64_t cgvec_prefetch_k_filtered(uint64_t limit);
 void cgvec_normalize_scores(float* scores, size_t n);

@@ -234,3 +234,28 @@ def test_enable_gpu_switch_and_device_list(cg, monkeypatch):
             with pytest.raises(cg.CgvecError) as e:
                 cg.Index.from_env(64)
             assert e.value.code == cg.ERR_NO_DEVICE
+
+
+def test_auto_cost_model_agrees_with_the_committed_measurements(cg):
+    """CGVEC_PATH_AUTO's cost model (host_tensor.inl) against the B200 measurements it was fitted to
+    (profiles/r02_exact_vs_tensor_small_batches.txt, tools/bench_paths.py): it must pick the measured-faster family wherever the
+    two differ by more than 15 %, and its estimates must stay within a factor 1.5 of the measured call times."""
+    import json
+    path = os.path.join(ROOT, "profiles", "r02_exact_vs_tensor_small_batches.txt")
+    checked = picked = 0
+    for line in open(path):
+        line = line.strip()
+        if not line.startswith("{"):
+            continue
+        r = json.loads(line)
+        if r["nq"] < 2 or r.get("exact_ms") is None or r.get("tensor_ms") is None:
+            continue                                            # batch-1 stays on the exact-order kernel by rule, not by cost
+        dt = cg.F32 if r["dtype"] == "f32" else cg.F16
+        te, tt = cg.path_cost_model(dt, 768, r["rows"], r["nq"], 128)
+        assert r["exact_ms"] / 1.5 <= te <= r["exact_ms"] * 1.5, (r, te)
+        assert r["tensor_ms"] / 1.5 <= tt <= r["tensor_ms"] * 1.5, (r, tt)
+        checked += 1
+        if max(r["exact_ms"], r["tensor_ms"]) > 1.15 * min(r["exact_ms"], r["tensor_ms"]):
+            assert (tt < te) == (r["tensor_ms"] < r["exact_ms"]), (r, te, tt)
+            picked += 1
+    assert checked >= 30 and picked >= 20
