@@ -116,6 +116,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(inside)}
 
 
+def agreed_count(max_over_ranks, local_seconds_per_unit, target_s, lo=1, hi=500):
+    """How many units (pre-warm rounds, timed batches) fit `target_s`, identical on every rank: the estimate is reduced with MAX
+    over the ranks BEFORE it sizes the loop.  Every search of a sharded index carries one exchange step, so a loop count taken from
+    a rank's own clock desynchronises the ranks (tests/test_sharded_gloo.py::test_loop_counts_are_agreed_over_the_ranks)."""
+    est = max_over_ranks(float(local_seconds_per_unit))
+    return int(min(hi, max(lo, np.ceil(target_s / max(est, 1e-5)))))
+
+
 def host_queries(oracle, n, d, salt=0):
     return oracle.synth_rows(SEED_QUERIES + salt, 0, n, d, True, False)
 
@@ -535,8 +543,7 @@ def run_b200(args, rank, world, local_rank):
         for i in range(args.warmup):
             step_device(i)
         torch.cuda.synchronize()
-        round_s = env.max_over_ranks(time.perf_counter() - t_pre)
-        rounds = int(min(500, max(1, np.ceil(0.25 / max(round_s, 1e-5)))))
+        rounds = agreed_count(env.max_over_ranks, time.perf_counter() - t_pre, 0.25)
         for _ in range(rounds):
             for i in range(args.warmup):
                 step_device(i)

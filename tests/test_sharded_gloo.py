@@ -62,3 +62,42 @@ def test_two_rank_gloo_merge_equals_single_process(oracle, metric_name):
             gi, gs = out[r]
             assert gi == want_idx.tolist()
             assert gs == want_sc.tobytes()
+
+
+def _worker_counts(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def max_over_ranks(x):
+            t = torch.tensor([x], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        # every rank measured a different time per round (its own clock): the loop count must still be the same everywhere
+        local = [0.0013, 0.0021][rank]
+        out[rank] = [bench.agreed_count(max_over_ranks, local * f, 0.25) for f in (1.0, 0.37, 40.0, 1e-9)]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loop_counts_are_agreed_over_the_ranks():
+    """bench.py sizes its pre-warm (and the batched configs' timed regions) from a measured time per unit.  On a sharded index every
+    search carries an exchange step, so all ranks must issue the same number of searches: a per-rank wall-clock loop ran different
+    counts at 8 GPUs in r02 and the surplus steps timed out in the exchange (profiles/r02_bench_n8_prewarm_failure.txt)."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        port = 29500 + (os.getpid() % 1000) + 7
+        procs = [ctx.Process(target=_worker_counts, args=(r, world, port, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(180)
+            assert p.exitcode == 0
+        assert out[0] == out[1]
+        assert out[0][0] == int(np.ceil(0.25 / 0.0021)) and out[0][2] == 3 and out[0][3] == 500      # sized by the SLOWEST rank, clamped
