@@ -155,6 +155,47 @@ private:
     uint32_t dim_;
 };
 
+// The serving loop of the reference is one search_similar per query (traits.rs:11-16; SemanticSearch::search_by_embedding,
+// search.rs:91-144).  A ResidentSession serves those calls with the scan kernel RESIDENT on the GPU between them (cgvec_serve_*):
+// same results as B200VectorStore::search_similar / top_k, no kernel launch per query.  The store must outlive the session and
+// may not be written to while the session is open (the library refuses both).
+class ResidentSession {
+public:
+    ResidentSession(std::shared_ptr<B200VectorStore> store, size_t limit, cgvec_metric metric = CGVEC_COSINE)
+        : store_(std::move(store)), k_(limit) {
+        check(cgvec_serve_open(store_->handle(), (uint32_t)limit, metric, &s_));
+    }
+    ~ResidentSession() { cgvec_serve_close(s_); }
+    ResidentSession(const ResidentSession&) = delete;
+    ResidentSession& operator=(const ResidentSession&) = delete;
+
+    std::vector<NodeId> search_similar(const std::vector<float>& q) {
+        if (q.size() != store_->dimension()) throw Error(CGVEC_ERR_BAD_DIM, "Query dimension mismatch");
+        std::vector<std::array<uint8_t, 16>> ids(k_);
+        uint32_t count = 0;
+        check(cgvec_serve_search(s_, q.data(), nullptr, reinterpret_cast<uint8_t(*)[16]>(ids.data()), nullptr, &count));
+        std::vector<NodeId> out(count);
+        for (uint32_t i = 0; i < count; ++i) out[i].bytes = ids[i];
+        return out;
+    }
+    std::vector<std::pair<uint64_t, float>> top_k(const std::vector<float>& q) {
+        if (q.size() != store_->dimension()) throw Error(CGVEC_ERR_BAD_DIM, "Query dimension mismatch");
+        std::vector<uint64_t> rows(k_);
+        std::vector<float> scores(k_);
+        uint32_t count = 0;
+        check(cgvec_serve_search(s_, q.data(), rows.data(), nullptr, scores.data(), &count));
+        std::vector<std::pair<uint64_t, float>> out(count);
+        for (uint32_t i = 0; i < count; ++i) out[i] = {rows[i], scores[i]};
+        return out;
+    }
+    void pause() { check(cgvec_serve_pause(s_)); }               // free the SMs now; the next call restarts the kernel
+
+private:
+    std::shared_ptr<B200VectorStore> store_;
+    size_t k_;
+    cgvec_server* s_ = nullptr;
+};
+
 // trait SurrealVectorBackend (surreal_store.rs:11-22)
 class SurrealVectorBackend {
 public:

@@ -74,6 +74,15 @@ int main(int argc, char** argv) {
                 std::cout << " " << c.node_id.to_string() << "/" << c.chunk_id.to_string() << "/" << std::hexfloat << c.vector_score << std::defaultfloat;
             std::cout << "\ncandidates_bad_limit " << stage.candidates(q, 0).size() << " " << stage.candidates(q, 1000).size() << "\n";
         }
+        if (n_devices == 1) {   // the same queries through a resident session (kernel stays on the GPU between the calls)
+            cgvec::ResidentSession session(store, limit);
+            session.top_k(q);
+            std::cout << "session_top_k";
+            for (auto& [row, score] : session.top_k(q)) std::cout << " " << row << ":" << std::hexfloat << score << std::defaultfloat;
+            std::cout << "\nsession_similar";
+            for (auto& id : session.search_similar(q)) std::cout << " " << id.to_string();
+            std::cout << "\n";
+        }
         auto missing = store->get_embedding(cgvec::NodeId::from_u64(123456789));
         std::cout << "missing " << (missing ? "some" : "none") << "\n";
         try {

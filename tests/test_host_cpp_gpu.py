@@ -56,6 +56,9 @@ def test_host_mirror_matches_oracle(cg, oracle):
     assert [c[0] for c in got_c] == [f"00000000-0000-0000-0000-{1000000 + i // 3:012x}" for i, _ in want_c]
     assert np.float32([float.fromhex(c[2]) for c in got_c]).tobytes() == np.float32([s for _, s in want_c]).tobytes()
     assert lines["candidates_bad_limit"].split() == ["30", "30"]                   # limit outside 1..100 -> safe_limit 10
+    # ResidentSession (cgvec_serve_*) gives the same answers as the launch-per-query calls
+    assert lines["session_top_k"] == lines["top_k"]
+    assert lines["session_similar"] == lines["search_similar"]
     assert lines["missing"] == "none"
     assert lines["baddim"] == str(cg.ERR_BAD_DIM)
 
